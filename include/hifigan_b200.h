@@ -1,0 +1,159 @@
+/*
+ * hifigan_b200.h — C ABI of the B200-native HiFi-GAN generator (libhifigan_b200.so).
+ *
+ * The reference (diff7/tts-king) has no FFI: its boundary for this path is the Python
+ * nn.Module protocol of hifi/models.py::Generator and the hifiapi.py::HIFIapi wrapper
+ * (SURVEY.md §8b).  This header is the C surface that sits directly under that protocol;
+ * tts_king_b200/hifi/models.py binds it with ctypes (see INTEGRATION.md for the stub a
+ * reference maintainer would add).  Every entry point names the reference interface it
+ * stands in for.
+ *
+ * Conventions: extern "C"; plain pointers and sizes only (no torch / C++ types); every
+ * function returns 0 on success or a negative HG_E* code, with a thread-local message from
+ * hg_last_error(); nothing throws; hg_forward performs no device allocation — the caller owns
+ * the mel, the output and the workspace (PyTorch's caching allocator in the Python binding),
+ * and all work is enqueued on the caller's stream.  A plan is immutable after
+ * hg_plan_finalize; concurrent hg_forward calls on distinct streams + workspaces are safe.
+ *
+ * There is no CPU fallback: every compute entry point runs hand-written sm_100a kernels and
+ * fails with HG_ENODEVICE / HG_ECUDA otherwise.
+ */
+#ifndef HIFIGAN_B200_H_
+#define HIFIGAN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HG_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define HG_API __attribute__((visibility("default")))
+#else
+#define HG_API
+#endif
+
+#define HG_MAX_UPS 8
+#define HG_MAX_KERNELS 8
+#define HG_MAX_DIL 4
+
+/* error codes */
+#define HG_OK 0
+#define HG_EINVAL (-1)    /* bad argument / shape mismatch (RuntimeError in the reference) */
+#define HG_ENODEVICE (-2) /* no sm_100 device */
+#define HG_ECUDA (-3)     /* CUDA runtime / driver error */
+#define HG_ESTATE (-4)    /* call order: missing weights, plan not finalized, ... */
+#define HG_ENOMEM (-5)    /* workspace too small / host allocation failed */
+
+/* arithmetic mode of the contraction (north_star: an fp32 path within 1e-4 of the reference and
+ * a bf16 path with SNR >= 40 dB) */
+#define HG_PREC_BF16 0      /* bf16 operands, fp32 accumulate (TMEM), fp32 residual stream */
+#define HG_PREC_FP32 1      /* fp32-accurate on tensor cores: bf16x3 split operands (hi/lo)    */
+#define HG_PREC_FP32_FFMA 2 /* exact fp32 FFMA on CUDA cores (slow; on-device cross-check)      */
+
+#define HG_OUT_F32 0 /* Generator.forward: float wav in [-1,1]           hifi/models.py:199 */
+#define HG_OUT_I16 1 /* HIFIapi.generate: wav*scale, truncating int16     hifiapi.py:50-51  */
+
+/*
+ * The fields Generator.__init__ reads from `h` — hifi/models.py:150-181 (values for V1 in
+ * config.yaml:16,25-29).  resblock_type: 1 = ResBlock1 (hifi/models.py:12-101, uses 3
+ * dilations), 2 = ResBlock2 (:104-143, uses 2).
+ */
+typedef struct HgConfig {
+  int32_t num_mels;                 /* 80, hard-coded at hifi/models.py:153 */
+  int32_t upsample_initial_channel;
+  int32_t num_upsamples;
+  int32_t upsample_rates[HG_MAX_UPS];
+  int32_t upsample_kernel_sizes[HG_MAX_UPS];
+  int32_t num_kernels;
+  int32_t resblock_kernel_sizes[HG_MAX_KERNELS];
+  int32_t resblock_dilation_sizes[HG_MAX_KERNELS][HG_MAX_DIL];
+  int32_t resblock_type;
+} HgConfig;
+
+typedef struct HgPlan HgPlan;
+
+HG_API int hg_abi_version(void);
+
+/* Message for the last failing call on this thread ("" if none). */
+HG_API const char* hg_last_error(void);
+
+/* Number of visible sm_100 devices (0 if none / no driver).  Never fails. */
+HG_API int hg_device_count(void);
+
+/* Generator.__init__(h) — hifi/models.py:147-183: fixes the layer list for `cfg` on `device`. */
+HG_API int hg_plan_create(const HgConfig* cfg, int device, HgPlan** plan);
+
+/*
+ * load_state_dict + remove_weight_norm — hifiapi.py:20-28, hifi/models.py:203-210.
+ * `name` is the state_dict prefix ("conv_pre", "ups.1", "resblocks.4.convs2.0", "conv_post");
+ * `weight` is the FOLDED fp32 tensor in the reference's own layout on the HOST
+ * (Conv1d [C_out,C_in,k], ConvTranspose1d [C_in,C_out,k]); `bias` [C_out].  The library repacks
+ * (tap-major, K-major, bf16 hi/lo, 128B-swizzled tiles) and uploads.
+ */
+HG_API int hg_plan_upload_weight(HgPlan* plan, const char* name, const float* weight,
+                          const int64_t* shape, int ndim, const float* bias, int64_t bias_len);
+
+/* Checks every layer has weights; after this the plan is immutable. */
+HG_API int hg_plan_finalize(HgPlan* plan);
+
+/* Bytes of device scratch hg_forward needs for a [B,80,T] input in `precision`. */
+HG_API int hg_workspace_bytes(const HgPlan* plan, int B, int T, int precision, size_t* bytes);
+
+/* Kernel launches one hg_forward(B,T,precision) enqueues (bench.py's gpu_launches). */
+HG_API int hg_forward_launches(const HgPlan* plan, int B, int T, int precision, int* launches);
+
+/*
+ * Generator.forward(x) — hifi/models.py:185-201 (and, with HG_OUT_I16, the tail of
+ * HIFIapi.generate, hifiapi.py:50-51).
+ *   mel      device fp32, logical shape [B, num_mels, T] with ELEMENT strides (sB, sC, sT) — the
+ *            caller's tensor may be the non-contiguous transpose of a time-major [B,T,80]
+ *            (tts_king.py:48); it is read in place, never modified.
+ *   out      device, [B, 1, T*prod(rates)] contiguous; float (HG_OUT_F32) or int16 (HG_OUT_I16,
+ *            value = (int16)trunc(wav * out_scale) with numpy's wrap-around cast).
+ *   workspace  device scratch of at least hg_workspace_bytes(); 1024-byte aligned.
+ *   stream   cudaStream_t (as void*); all kernels are enqueued there, nothing synchronizes.
+ */
+HG_API int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC, int64_t sT, int B, int T,
+               void* out, int out_dtype, float out_scale, int precision, void* workspace,
+               size_t workspace_bytes, void* stream);
+
+/* Frees device weights and host state. */
+HG_API int hg_plan_destroy(HgPlan* plan);
+
+/*
+ * Single-layer entry points for op-level parity tests (SURVEY.md §4 tier T1).  They run the same
+ * kernels hg_forward uses on one layer.  Layout is the library's native channels-last:
+ *   x  device fp32 [B][L][C_in]      y  device fp32 [B][L_out][C_out]
+ * `weight`/`bias` are HOST fp32 in the reference layout.  in_slope: leaky_relu slope applied to
+ * x before the convolution (1.0 = none).  residual: optional device fp32 [B][L_out][C_out] added
+ * to the result.  Allocates temporaries and synchronizes — not a hot-path call.
+ *   hg_op_conv1d            torch Conv1d(C_in,C_out,k,1,dilation=d,padding=get_padding(k,d))
+ *                           as built at hifi/models.py:19-81,152-154
+ *   hg_op_conv_transpose1d  torch ConvTranspose1d(C_in,C_out,k,s,padding=(k-s)//2),
+ *                           hifi/models.py:161-171
+ *   hg_op_conv_post         leaky_relu(0.01) -> Conv1d(C,1,7,padding=3) -> tanh,
+ *                           hifi/models.py:197-199; y device fp32 [B][L]
+ */
+HG_API int hg_op_conv1d(int device, int precision, const float* x, int B, int L, int C_in,
+                 const float* weight, const float* bias, int C_out, int k, int dilation,
+                 float in_slope, const float* residual, float* y, void* stream);
+HG_API int hg_op_conv_transpose1d(int device, int precision, const float* x, int B, int L, int C_in,
+                           const float* weight, const float* bias, int C_out, int k, int stride,
+                           float in_slope, float* y, void* stream);
+HG_API int hg_op_conv_post(int device, const float* x, int B, int L, int C, const float* weight,
+                    const float* bias, float* y, void* stream);
+
+/*
+ * Debug / bring-up: runs the tcgen05 descriptor self-test (shifted-row UMMA descriptors against a
+ * CUDA-core reference) and writes a report into `buf`.  Returns the number of failing cases.
+ */
+HG_API int hg_selftest_tcgen05(int device, char* buf, size_t buf_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIFIGAN_B200_H_ */

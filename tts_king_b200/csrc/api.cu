@@ -1,0 +1,723 @@
+// api.cu — C ABI of libhifigan_b200 (include/hifigan_b200.h): plan construction, weight
+// repacking, the layer schedule of Generator.forward (reference hifi/models.py:185-201) and the
+// op-level / self-test entry points.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "plan.h"
+
+namespace hg {
+// kernels.cu-side launchers
+size_t conv_tc_smem_bytes(int n_t, int kc, bool split, int slab_rows, int nbuf, int stages);
+cudaError_t launch_conv_tc(int n_t, int kc, int ms, bool split, const CUtensorMap& mh, const CUtensorMap& ml,
+                           const TcConvParams& p, int n_blocks, size_t smem, cudaStream_t st);
+cudaError_t launch_conv_ffma(const FfmaConvParams& p, cudaStream_t st);
+cudaError_t launch_conv_post(const float* x, int B, int L, int C, const float* w_tapmajor, float bias, float* out_f32,
+                             int16_t* out_i16, float out_scale, cudaStream_t st);
+cudaError_t launch_mel_to_operand(const float* mel, long long sB, long long sC, long long sT, int B, int C, int T,
+                                  int c_pad, int a_fmt, void* a0, void* a1, cudaStream_t st);
+cudaError_t launch_f32_to_operand(const float* x, long long n, float slope, int a_fmt, void* a0, void* a1,
+                                  cudaStream_t st);
+int run_tcgen05_selftest(char* buf, size_t len);
+}  // namespace hg
+
+using namespace hg;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) return fail(HG_ECUDA, "%s: %s", #expr, cudaGetErrorString(_e));   \
+  } while (0)
+
+extern "C" int hg_abi_version(void) { return HG_ABI_VERSION; }
+extern "C" const char* hg_last_error(void) { return g_err.c_str(); }
+
+extern "C" int hg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int d = 0; d < n; ++d) {
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, d) == cudaSuccess && pr.major == 10) ++ok;
+  }
+  return ok;
+}
+
+static int check_device(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(HG_ENODEVICE, "no CUDA device visible; libhifigan_b200 has no CPU fallback");
+  }
+  if (device < 0 || device >= n) return fail(HG_EINVAL, "device %d out of range (0..%d)", device, n - 1);
+  cudaDeviceProp pr;
+  CUDA_TRY(cudaGetDeviceProperties(&pr, device));
+  if (pr.major != 10)
+    return fail(HG_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, pr.major, pr.minor);
+  return HG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA descriptor encoding through the driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 operand plane [B][L][cpitch] -> 3-D map with box {kc, box_rows, 1}; rows outside [0,L) read
+// as zero (that is the convolution's zero padding, and it keeps batch items from bleeding).
+static int make_operand_map(HgPlan* plan, const void* ptr, int L, int B, int cpitch, int kc, int box_rows,
+                            CUtensorMap* out) {
+  MapKey key(ptr, L, B, cpitch, kc, box_rows);
+  {
+    std::lock_guard<std::mutex> g(plan->mu);
+    auto it = plan->maps.find(key);
+    if (it != plan->maps.end()) { *out = it->second; return HG_OK; }
+  }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(HG_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cpitch), static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(cpitch) * 2, static_cast<cuuint64_t>(L) * cpitch * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(kc), static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(HG_ECUDA, "cuTensorMapEncodeTiled failed (%d) for L=%d B=%d C=%d kc=%d box=%d", static_cast<int>(r), L,
+                B, cpitch, kc, box_rows);
+  {
+    std::lock_guard<std::mutex> g(plan->mu);
+    if (plan->maps.size() > 4096) plan->maps.clear();
+    plan->maps[key] = m;
+  }
+  *out = m;
+  return HG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layer table
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+static void setup_gemm_view(Layer& l) {
+  if (l.kind == L_CONV) {
+    l.ntaps = l.k;
+    for (int j = 0; j < l.k; ++j) l.tap_off[j] = j * l.dil - l.pad;
+    l.n_total = l.cout;
+  } else if (l.kind == L_CONVT) {
+    l.ntaps = (l.k + l.stride - 1) / l.stride;
+    for (int m = 0; m < l.ntaps; ++m) l.tap_off[m] = -m;
+    l.n_total = l.stride * l.cout;
+  }
+  l.tc = false;
+  if (l.kind == L_POST) return;
+  int cin_pad = 0;
+  if (l.cin % 32 == 0) cin_pad = l.cin;
+  else if (l.cin >= 64) cin_pad = (l.cin + 63) / 64 * 64;  // conv_pre: 80 mel bins -> 128
+  if (cin_pad && l.n_total % 32 == 0 && l.cout % 4 == 0 && l.ntaps <= kMaxTaps) {
+    l.tc = true;
+    l.cin_pad = cin_pad;
+    l.kc = cin_pad % 64 == 0 ? 64 : 32;
+    l.nc = cin_pad / l.kc;
+    l.n_tile = l.n_total % 256 == 0 ? 256 : l.n_total % 128 == 0 ? 128 : l.n_total % 64 == 0 ? 64 : 32;
+    l.n_blocks = l.n_total / l.n_tile;
+  } else {
+    l.cin_pad = l.cin;
+  }
+}
+
+static Layer make_conv(const std::string& name, int cin, int cout, int k, int dil) {
+  Layer l;
+  l.name = name; l.kind = L_CONV; l.cin = cin; l.cout = cout; l.k = k; l.dil = dil;
+  l.pad = (k * dil - dil) / 2;  // get_padding, hifi/vocoder/utils.py:36-37
+  setup_gemm_view(l);
+  return l;
+}
+static Layer make_convT(const std::string& name, int cin, int cout, int k, int stride) {
+  Layer l;
+  l.name = name; l.kind = L_CONVT; l.cin = cin; l.cout = cout; l.k = k; l.stride = stride;
+  l.pad = (k - stride) / 2;  // hifi/models.py:169
+  setup_gemm_view(l);
+  return l;
+}
+
+static int rb_dilations(const HgConfig& c) { return c.resblock_type == 1 ? 3 : 2; }
+
+extern "C" int hg_plan_create(const HgConfig* cfg, int device, HgPlan** out) {
+  if (!cfg || !out) return fail(HG_EINVAL, "null argument");
+  *out = nullptr;
+  if (cfg->num_upsamples < 1 || cfg->num_upsamples > HG_MAX_UPS || cfg->num_kernels < 1 ||
+      cfg->num_kernels > HG_MAX_KERNELS || cfg->num_mels < 1 || cfg->upsample_initial_channel < 1 ||
+      (cfg->resblock_type != 1 && cfg->resblock_type != 2))
+    return fail(HG_EINVAL, "bad HgConfig");
+  if ((cfg->upsample_initial_channel >> cfg->num_upsamples) < 1)
+    return fail(HG_EINVAL, "upsample_initial_channel too small for %d upsamplers", cfg->num_upsamples);
+  int rc = check_device(device);
+  if (rc) return rc;
+  HgPlan* p = new HgPlan();
+  p->cfg = *cfg;
+  p->device = device;
+  cudaDeviceProp pr;
+  if (cudaGetDeviceProperties(&pr, device) == cudaSuccess) p->sm_count = pr.multiProcessorCount;
+  p->desc_mode = env_int("HG_DESC_MODE", 1);
+  p->force_ms = env_int("HG_TC_MS", 0);
+  p->force_stages = env_int("HG_TC_STAGES", 0);
+  p->force_ffma = env_int("HG_FORCE_FFMA", 0) != 0;
+  const int uic = cfg->upsample_initial_channel;
+  p->layers.push_back(make_conv("conv_pre", cfg->num_mels, uic, 7, 1));
+  for (int i = 0; i < cfg->num_upsamples; ++i) {
+    if (cfg->upsample_kernel_sizes[i] < cfg->upsample_rates[i]) {
+      delete p;
+      return fail(HG_EINVAL, "upsample kernel < rate is not supported");
+    }
+    p->layers.push_back(make_convT("ups." + std::to_string(i), uic >> i, uic >> (i + 1),
+                                   cfg->upsample_kernel_sizes[i], cfg->upsample_rates[i]));
+  }
+  const int D = rb_dilations(*cfg);
+  int ch = uic;
+  for (int i = 0; i < cfg->num_upsamples; ++i) {
+    ch = uic >> (i + 1);
+    for (int j = 0; j < cfg->num_kernels; ++j) {
+      const std::string base = "resblocks." + std::to_string(i * cfg->num_kernels + j);
+      const int k = cfg->resblock_kernel_sizes[j];
+      if (k < 1 || k > kMaxTaps || (k & 1) == 0) {
+        delete p;
+        return fail(HG_EINVAL, "resblock kernel size %d unsupported (odd, <= %d)", k, kMaxTaps);
+      }
+      if (cfg->resblock_type == 1) {
+        for (int m = 0; m < D; ++m)
+          p->layers.push_back(make_conv(base + ".convs1." + std::to_string(m), ch, ch, k, cfg->resblock_dilation_sizes[j][m]));
+        for (int m = 0; m < D; ++m) p->layers.push_back(make_conv(base + ".convs2." + std::to_string(m), ch, ch, k, 1));
+      } else {
+        for (int m = 0; m < D; ++m)
+          p->layers.push_back(make_conv(base + ".convs." + std::to_string(m), ch, ch, k, cfg->resblock_dilation_sizes[j][m]));
+      }
+    }
+  }
+  Layer post;
+  post.name = "conv_post"; post.kind = L_POST; post.cin = ch; post.cout = 1; post.k = 7; post.pad = 3;
+  p->layers.push_back(post);
+  for (size_t i = 0; i < p->layers.size(); ++i) p->by_name[p->layers[i].name] = static_cast<int>(i);
+  *out = p;
+  return HG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight repacking
+static inline uint16_t f32_to_bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);  // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+static inline float bf16_to_f32(uint16_t h) {
+  uint32_t u = static_cast<uint32_t>(h) << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// GEMM-view weight Wg(tap, n, c) from the reference layouts.
+static inline float gemm_weight(const Layer& l, const float* W, int t, int n, int c) {
+  if (c >= l.cin) return 0.f;
+  if (l.kind == L_CONV) return W[(static_cast<size_t>(n) * l.cin + c) * l.k + t];
+  const int r = n / l.cout, o = n % l.cout;
+  const int j = r + l.stride * t;
+  return j < l.k ? W[(static_cast<size_t>(c) * l.cout + o) * l.k + j] : 0.f;
+}
+
+static int upload(const void* host, size_t bytes, void** dev) {
+  CUDA_TRY(cudaMalloc(dev, bytes));
+  CUDA_TRY(cudaMemcpy(*dev, host, bytes, cudaMemcpyHostToDevice));
+  return HG_OK;
+}
+
+static void free_layer(Layer& l) {
+  cudaFree(l.w_hi); cudaFree(l.w_lo); cudaFree(l.w_ffma); cudaFree(l.bias); cudaFree(l.w_post);
+  l.w_hi = l.w_lo = nullptr; l.w_ffma = nullptr; l.bias = nullptr; l.w_post = nullptr;
+  l.loaded = false;
+}
+
+static int pack_layer(Layer& l, const float* W, const float* bias) {
+  int rc;
+  if (l.kind == L_POST) {
+    std::vector<float> wp(static_cast<size_t>(l.k) * l.cin);
+    for (int j = 0; j < l.k; ++j)
+      for (int c = 0; c < l.cin; ++c) wp[static_cast<size_t>(j) * l.cin + c] = W[static_cast<size_t>(c) * l.k + j];
+    if ((rc = upload(wp.data(), wp.size() * 4, reinterpret_cast<void**>(&l.w_post)))) return rc;
+    l.bias_post = bias[0];
+    l.loaded = true;
+    return HG_OK;
+  }
+  std::vector<float> bfull(l.n_total);
+  for (int n = 0; n < l.n_total; ++n) bfull[n] = bias[n % l.cout];
+  if ((rc = upload(bfull.data(), bfull.size() * 4, reinterpret_cast<void**>(&l.bias)))) return rc;
+  {  // CUDA-core layout [tap][cin][n_total]
+    std::vector<float> wf(static_cast<size_t>(l.ntaps) * l.cin * l.n_total);
+    for (int t = 0; t < l.ntaps; ++t)
+      for (int c = 0; c < l.cin; ++c)
+        for (int n = 0; n < l.n_total; ++n)
+          wf[(static_cast<size_t>(t) * l.cin + c) * l.n_total + n] = gemm_weight(l, W, t, n, c);
+    if ((rc = upload(wf.data(), wf.size() * 4, reinterpret_cast<void**>(&l.w_ffma)))) return rc;
+  }
+  if (l.tc) {  // swizzled bf16 tiles [n_blk][chunk][tap][n_tile rows][kc], hi and lo planes
+    const int rowb = l.kc * 2;
+    const size_t tile = static_cast<size_t>(l.n_tile) * rowb;
+    const size_t total = tile * l.n_blocks * l.nc * l.ntaps;
+    std::vector<uint8_t> hi(total), lo(total);
+    for (int nb = 0; nb < l.n_blocks; ++nb)
+      for (int c = 0; c < l.nc; ++c)
+        for (int t = 0; t < l.ntaps; ++t) {
+          const size_t base = ((static_cast<size_t>(nb) * l.nc + c) * l.ntaps + t) * tile;
+          for (int row = 0; row < l.n_tile; ++row) {
+            const int swz = l.kc == 64 ? (row & 7) : ((row >> 1) & 3);
+            for (int kk = 0; kk < l.kc; ++kk) {
+              const float v = gemm_weight(l, W, t, nb * l.n_tile + row, c * l.kc + kk);
+              const uint16_t h = f32_to_bf16_rn(v);
+              const uint16_t lw = f32_to_bf16_rn(v - bf16_to_f32(h));
+              const size_t off = base + static_cast<size_t>(row) * rowb + (((kk >> 3) ^ swz) << 4) + ((kk & 7) << 1);
+              memcpy(&hi[off], &h, 2);
+              memcpy(&lo[off], &lw, 2);
+            }
+          }
+        }
+    if ((rc = upload(hi.data(), total, reinterpret_cast<void**>(&l.w_hi)))) return rc;
+    if ((rc = upload(lo.data(), total, reinterpret_cast<void**>(&l.w_lo)))) return rc;
+  }
+  l.loaded = true;
+  return HG_OK;
+}
+
+extern "C" int hg_plan_upload_weight(HgPlan* plan, const char* name, const float* weight, const int64_t* shape,
+                                     int ndim, const float* bias, int64_t bias_len) {
+  if (!plan || !name || !weight || !shape || !bias) return fail(HG_EINVAL, "null argument");
+  if (plan->finalized) return fail(HG_ESTATE, "plan is finalized (immutable)");
+  auto it = plan->by_name.find(name);
+  if (it == plan->by_name.end()) return fail(HG_EINVAL, "unexpected key in state_dict: %s", name);
+  Layer& l = plan->layers[it->second];
+  int64_t want[3];
+  if (l.kind == L_CONVT) { want[0] = l.cin; want[1] = l.cout; want[2] = l.k; }
+  else { want[0] = l.cout; want[1] = l.cin; want[2] = l.k; }
+  if (ndim != 3 || shape[0] != want[0] || shape[1] != want[1] || shape[2] != want[2])
+    return fail(HG_EINVAL, "size mismatch for %s.weight: expected [%lld,%lld,%lld]", name,
+                static_cast<long long>(want[0]), static_cast<long long>(want[1]), static_cast<long long>(want[2]));
+  if (bias_len != l.cout) return fail(HG_EINVAL, "size mismatch for %s.bias: expected [%d]", name, l.cout);
+  CUDA_TRY(cudaSetDevice(plan->device));
+  if (l.loaded) free_layer(l);
+  return pack_layer(l, weight, bias);
+}
+
+extern "C" int hg_plan_finalize(HgPlan* plan) {
+  if (!plan) return fail(HG_EINVAL, "null plan");
+  for (auto& l : plan->layers)
+    if (!l.loaded) return fail(HG_ESTATE, "missing key in state_dict: %s", l.name.c_str());
+  plan->finalized = true;
+  return HG_OK;
+}
+
+extern "C" int hg_plan_destroy(HgPlan* plan) {
+  if (!plan) return HG_OK;
+  cudaSetDevice(plan->device);
+  for (auto& l : plan->layers) free_layer(l);
+  delete plan;
+  return HG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launching one GEMM-shaped layer
+struct OperandBuf {
+  void* a0 = nullptr;
+  void* a1 = nullptr;
+};
+
+static int a_fmt_of(int precision) {
+  return precision == HG_PREC_BF16 ? A_BF16 : precision == HG_PREC_FP32 ? A_BF16_SPLIT : A_F32;
+}
+
+static bool use_tc(const HgPlan* plan, const Layer& l, int precision) {
+  return l.tc && precision != HG_PREC_FP32_FFMA && !plan->force_ffma;
+}
+
+static TcTiling choose_tiling(const HgPlan* plan, const Layer& l, bool split) {
+  TcTiling t;
+  int min_off = l.tap_off[0], max_off = l.tap_off[0];
+  for (int j = 1; j < l.ntaps; ++j) {
+    min_off = std::min(min_off, l.tap_off[j]);
+    max_off = std::max(max_off, l.tap_off[j]);
+  }
+  t.min_off = min_off;
+  const int span = max_off - min_off;
+  int ms = l.n_tile == 256 ? 1 : l.n_tile == 128 ? 2 : l.n_tile == 64 ? 2 : 4;
+  if (plan->force_ms) ms = plan->force_ms;
+  while (ms * l.n_tile > 512) ms >>= 1;
+  const size_t kMaxSmem = 227 * 1024;
+  for (;; ms >>= 1) {
+    t.ms = ms;
+    const int need = ms * 128 + span;
+    t.nboxes = (need + 255) / 256;
+    t.box_rows = (((need + t.nboxes - 1) / t.nboxes) + 7) / 8 * 8;
+    t.slab_rows = t.nboxes * t.box_rows;
+    t.nbuf = l.nc > 1 ? 2 : 1;
+    const int total_stages = l.nc * l.ntaps * (split ? 2 : 1);
+    // weight ring: as deep as fits next to the slab while leaving room for a second resident CTA
+    // when that still gives >= 3 stages; otherwise use the whole SM.
+    int best = 0;
+    for (int target : {static_cast<int>(kMaxSmem / 2) - 1024, static_cast<int>(kMaxSmem)}) {
+      int s = 8;
+      while (s >= 2 && conv_tc_smem_bytes(l.n_tile, l.kc, split, t.slab_rows, t.nbuf, s) > static_cast<size_t>(target)) --s;
+      if (s >= 3 || (target == static_cast<int>(kMaxSmem) && s >= 2)) { best = s; break; }
+    }
+    if (plan->force_stages) best = plan->force_stages;
+    if (best >= 2 && conv_tc_smem_bytes(l.n_tile, l.kc, split, t.slab_rows, t.nbuf, best) <= kMaxSmem) {
+      t.stages = std::min(best, std::max(2, total_stages));
+      break;
+    }
+    if (ms == 1) { t.stages = 0; break; }  // does not fit at all
+  }
+  t.smem = conv_tc_smem_bytes(l.n_tile, l.kc, split, t.slab_rows, t.nbuf, t.stages);
+  return t;
+}
+
+// in: operand planes [B][L_in][cin_pad].  epi: fully populated except bias/a_fmt.
+static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_in, const OperandBuf& in, EpiParams epi,
+                     cudaStream_t st) {
+  const int rows = l.kind == L_CONVT ? L_in + 1 : L_in;
+  const long long L_out = l.kind == L_CONVT ? static_cast<long long>(L_in - 1) * l.stride - 2 * l.pad + l.k : L_in;
+  epi.bias = l.bias;
+  epi.a_fmt = a_fmt_of(precision);
+  epi.out_batch_stride = L_out * l.cout;
+  epi.out_extent = L_out * l.cout;
+  epi.out_row_stride = l.n_total;
+  epi.out_offset = l.kind == L_CONVT ? -static_cast<long long>(l.pad) * l.cout : 0;
+  if (use_tc(plan, l, precision)) {
+    const bool split = precision == HG_PREC_FP32;
+    TcTiling t = choose_tiling(plan, l, split);
+    if (t.stages >= 2) {
+      TcConvParams p;
+      memset(&p, 0, sizeof(p));
+      p.B = B; p.rows = rows;
+      p.tiles_per_item = (rows + t.ms * 128 - 1) / (t.ms * 128);
+      p.nc = l.nc; p.ntaps = l.ntaps;
+      for (int j = 0; j < l.ntaps; ++j) p.tap_row[j] = l.tap_off[j] - t.min_off;
+      p.min_off = t.min_off; p.slab_rows = t.slab_rows; p.box_rows = t.box_rows; p.nboxes = t.nboxes;
+      p.nbuf = t.nbuf; p.stages = t.stages; p.desc_mode = plan->desc_mode;
+      p.w_hi = l.w_hi; p.w_lo = l.w_lo; p.epi = epi;
+      CUtensorMap mh, ml;
+      int rc = make_operand_map(plan, in.a0, L_in, B, l.cin_pad, l.kc, t.box_rows, &mh);
+      if (rc) return rc;
+      ml = mh;
+      if (split && (rc = make_operand_map(plan, in.a1, L_in, B, l.cin_pad, l.kc, t.box_rows, &ml))) return rc;
+      cudaError_t e = launch_conv_tc(l.n_tile, l.kc, t.ms, split, mh, ml, p, l.n_blocks, t.smem, st);
+      if (e != cudaSuccess) return fail(HG_ECUDA, "conv_tc launch (%s): %s", l.name.c_str(), cudaGetErrorString(e));
+      return HG_OK;
+    }
+  }
+  FfmaConvParams f;
+  memset(&f, 0, sizeof(f));
+  f.B = B; f.L_in = L_in; f.rows = rows; f.cin = l.cin_pad; f.n_total = l.n_total; f.ntaps = l.ntaps;
+  for (int j = 0; j < l.ntaps; ++j) f.tap_off[j] = l.tap_off[j];
+  f.a0 = in.a0; f.a1 = in.a1; f.a_fmt = a_fmt_of(precision);
+  f.w = l.w_ffma; f.epi = epi;
+  if (l.cin_pad != l.cin) return fail(HG_ESTATE, "internal: padded operand on the CUDA-core path (%s)", l.name.c_str());
+  cudaError_t e = launch_conv_ffma(f, st);
+  if (e != cudaSuccess) return fail(HG_ECUDA, "conv_ffma launch (%s): %s", l.name.c_str(), cudaGetErrorString(e));
+  return HG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace
+struct Workspace {
+  float* F[3];
+  OperandBuf A[3];
+  OperandBuf mel;
+  size_t bytes;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// channel pitch of the mel operand: padded only when conv_pre runs on the tensor-core path
+static int mel_pitch(const HgPlan* plan, int precision) {
+  const Layer& pre = plan->layers[0];
+  return use_tc(plan, pre, precision) ? pre.cin_pad : pre.cin;
+}
+
+static int layout_workspace(const HgPlan* plan, int B, int T, int precision, void* base, Workspace* ws) {
+  const HgConfig& c = plan->cfg;
+  long long L = T;
+  long long max_e = static_cast<long long>(B) * T * c.upsample_initial_channel;
+  for (int i = 0; i < c.num_upsamples; ++i) {
+    const Layer& up = plan->layers[1 + i];
+    L = (L - 1) * up.stride - 2 * up.pad + up.k;
+    if (L < 1) return fail(HG_EINVAL, "input too short for upsampler %d", i);
+    max_e = std::max(max_e, static_cast<long long>(B) * L * up.cout);
+  }
+  const size_t fb = align_up(static_cast<size_t>(max_e) * 4, 1024);
+  const size_t plane = align_up(static_cast<size_t>(max_e) * 2, 1024);
+  const size_t ab = precision == HG_PREC_BF16 ? plane : precision == HG_PREC_FP32 ? 2 * plane : fb;
+  const size_t mel_e = static_cast<size_t>(B) * T * mel_pitch(plan, precision);
+  const size_t mplane = align_up(mel_e * 2, 1024);
+  const size_t mb = precision == HG_PREC_BF16 ? mplane : precision == HG_PREC_FP32 ? 2 * mplane : align_up(mel_e * 4, 1024);
+  uint8_t* p = static_cast<uint8_t*>(base);
+  size_t off = 0;
+  for (int i = 0; i < 3; ++i) { ws->F[i] = reinterpret_cast<float*>(p + off); off += fb; }
+  for (int i = 0; i < 3; ++i) {
+    ws->A[i].a0 = p + off;
+    ws->A[i].a1 = precision == HG_PREC_FP32 ? p + off + plane : nullptr;
+    off += ab;
+  }
+  ws->mel.a0 = p + off;
+  ws->mel.a1 = precision == HG_PREC_FP32 ? p + off + mplane : nullptr;
+  off += mb;
+  ws->bytes = off;
+  return HG_OK;
+}
+
+static int check_fwd_args(const HgPlan* plan, int B, int T, int precision) {
+  if (!plan) return fail(HG_EINVAL, "null plan");
+  if (!plan->finalized) return fail(HG_ESTATE, "plan not finalized");
+  if (B < 1 || T < 1) return fail(HG_EINVAL, "expected B >= 1 and T >= 1, got B=%d T=%d", B, T);
+  if (precision < HG_PREC_BF16 || precision > HG_PREC_FP32_FFMA) return fail(HG_EINVAL, "unknown precision %d", precision);
+  long long hop = 1;
+  for (int i = 0; i < plan->cfg.num_upsamples; ++i) hop *= plan->cfg.upsample_rates[i];
+  if (static_cast<long long>(T) * hop > 0x7fffffffLL) return fail(HG_EINVAL, "T*hop exceeds 2^31-1 samples");
+  return HG_OK;
+}
+
+extern "C" int hg_workspace_bytes(const HgPlan* plan, int B, int T, int precision, size_t* bytes) {
+  int rc = check_fwd_args(plan, B, T, precision);
+  if (rc) return rc;
+  if (!bytes) return fail(HG_EINVAL, "null bytes");
+  Workspace ws;
+  if ((rc = layout_workspace(plan, B, T, precision, nullptr, &ws))) return rc;
+  *bytes = ws.bytes;
+  return HG_OK;
+}
+
+extern "C" int hg_forward_launches(const HgPlan* plan, int B, int T, int precision, int* launches) {
+  int rc = check_fwd_args(plan, B, T, precision);
+  if (rc) return rc;
+  if (!launches) return fail(HG_EINVAL, "null launches");
+  *launches = static_cast<int>(plan->layers.size()) + 1;  // every layer + the mel repack
+  return HG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generator.forward — hifi/models.py:185-201
+extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC, int64_t sT, int B, int T, void* out,
+                          int out_dtype, float out_scale, int precision, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  int rc = check_fwd_args(plan, B, T, precision);
+  if (rc) return rc;
+  if (!mel || !out || !workspace) return fail(HG_EINVAL, "null buffer");
+  if (out_dtype != HG_OUT_F32 && out_dtype != HG_OUT_I16) return fail(HG_EINVAL, "unknown out_dtype %d", out_dtype);
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(HG_EINVAL, "workspace must be 1024-byte aligned");
+  Workspace ws;
+  if ((rc = layout_workspace(plan, B, T, precision, workspace, &ws))) return rc;
+  if (workspace_bytes < ws.bytes)
+    return fail(HG_ENOMEM, "workspace too small: %zu < %zu bytes", workspace_bytes, ws.bytes);
+  CUDA_TRY(cudaSetDevice(plan->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const HgConfig& c = plan->cfg;
+  const int fmt = a_fmt_of(precision);
+  const int U = c.num_upsamples, K = c.num_kernels, D = rb_dilations(c);
+  const float slope = 0.1f;  // LRELU_SLOPE, hifi/models.py:9
+
+  // mel [B,80,T] (any strides) -> channels-last operand
+  cudaError_t e = launch_mel_to_operand(mel, sB, sC, sT, B, c.num_mels, T, mel_pitch(plan, precision), fmt, ws.mel.a0,
+                                        ws.mel.a1, st);
+  if (e != cudaSuccess) return fail(HG_ECUDA, "mel_to_operand: %s", cudaGetErrorString(e));
+
+  // x = conv_pre(x)  :186 ; only leaky_relu(x) is consumed (by ups[0], :188-189)
+  int a_cur = 1;  // operand buffer holding leaky_relu(current x)
+  {
+    EpiParams ep; memset(&ep, 0, sizeof(ep));
+    ep.out_a0 = ws.A[a_cur].a0; ep.out_a1 = ws.A[a_cur].a1; ep.slope = slope;
+    if ((rc = run_layer(plan, plan->layers[0], precision, B, T, ws.mel, ep, st))) return rc;
+  }
+  int L = T;
+  int li = 1 + U;  // first resblock layer
+  float* x_final = nullptr;
+  for (int i = 0; i < U; ++i) {
+    const Layer& up = plan->layers[1 + i];
+    const bool last_stage = i == U - 1;
+    // x = ups[i](leaky_relu(x))  :188-189  -> residual stream F0 and operand A0
+    {
+      EpiParams ep; memset(&ep, 0, sizeof(ep));
+      ep.out_x = ws.F[0]; ep.out_a0 = ws.A[0].a0; ep.out_a1 = ws.A[0].a1; ep.slope = slope;
+      if ((rc = run_layer(plan, up, precision, B, L, ws.A[a_cur], ep, st))) return rc;
+    }
+    L = (L - 1) * up.stride - 2 * up.pad + up.k;
+    // xs = sum_j resblocks[i*K+j](x) ; x = xs / K   :190-196
+    for (int j = 0; j < K; ++j) {
+      int a_in = 0;          // operand of the block's running x (A0 = the shared stage input)
+      const float* res = ws.F[0];
+      for (int m = 0; m < D; ++m) {
+        const bool last_pair = m == D - 1;
+        int a_conv_in = a_in;
+        if (c.resblock_type == 1) {
+          // xt = c1(leaky_relu(x)); only leaky_relu(xt) is consumed  :90-92
+          const int a_t = 2;
+          EpiParams ep; memset(&ep, 0, sizeof(ep));
+          ep.out_a0 = ws.A[a_t].a0; ep.out_a1 = ws.A[a_t].a1; ep.slope = slope;
+          if ((rc = run_layer(plan, plan->layers[li + m], precision, B, L, ws.A[a_in], ep, st))) return rc;
+          a_conv_in = a_t;
+        }
+        const Layer& l2 = plan->layers[c.resblock_type == 1 ? li + D + m : li + m];
+        // x = c2(xt) + x  :93-94 (ResBlock2: x = c(leaky_relu(x)) + x  :136-138)
+        EpiParams ep; memset(&ep, 0, sizeof(ep));
+        ep.res = res; ep.slope = slope;
+        // next operand buffer must differ from the one this conv reads (neighbouring CTAs read halos)
+        const int a_next = (a_conv_in == 1) ? 2 : 1;
+        if (!last_pair) {
+          ep.out_x = ws.F[1]; ep.out_a0 = ws.A[a_next].a0; ep.out_a1 = ws.A[a_next].a1;
+          a_in = a_next;
+          res = ws.F[1];
+        } else {
+          // MRF combine fused into the block's last epilogue  :193-196
+          if (j > 0) ep.acc_in = ws.F[2];
+          if (j < K - 1) {
+            ep.out_x = ws.F[2];
+          } else {
+            if (K > 1) ep.post_div = static_cast<float>(K);
+            if (last_stage) {
+              ep.out_x = ws.F[1];  // conv_post applies its own leaky_relu(0.01)  :197
+              x_final = ws.F[1];
+            } else {
+              ep.out_a0 = ws.A[a_next].a0; ep.out_a1 = ws.A[a_next].a1;
+              a_cur = a_next;
+            }
+          }
+        }
+        if ((rc = run_layer(plan, l2, precision, B, L, ws.A[a_conv_in], ep, st))) return rc;
+      }
+      li += c.resblock_type == 1 ? 2 * D : D;
+    }
+  }
+  // x = tanh(conv_post(leaky_relu(x)))  :197-199  (+ optional int16 tail, hifiapi.py:50-51)
+  const Layer& post = plan->layers.back();
+  e = launch_conv_post(x_final, B, L, post.cin, post.w_post, post.bias_post,
+                       out_dtype == HG_OUT_F32 ? static_cast<float*>(out) : nullptr,
+                       out_dtype == HG_OUT_I16 ? static_cast<int16_t*>(out) : nullptr, out_scale, st);
+  if (e != cudaSuccess) return fail(HG_ECUDA, "conv_post: %s", cudaGetErrorString(e));
+  return HG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// op-level entry points (parity tier T1)
+static int op_layer(int device, int precision, Layer& l, const float* x, int B, int L, const float* weight,
+                    const float* bias, float in_slope, const float* residual, float* y, void* stream) {
+  int rc = check_device(device);
+  if (rc) return rc;
+  if (precision < HG_PREC_BF16 || precision > HG_PREC_FP32_FFMA) return fail(HG_EINVAL, "unknown precision");
+  CUDA_TRY(cudaSetDevice(device));
+  HgPlan plan;
+  plan.device = device;
+  plan.desc_mode = env_int("HG_DESC_MODE", 1);
+  plan.force_ms = env_int("HG_TC_MS", 0);
+  plan.force_stages = env_int("HG_TC_STAGES", 0);
+  plan.force_ffma = env_int("HG_FORCE_FFMA", 0) != 0;
+  if ((rc = pack_layer(l, weight, bias))) { free_layer(l); return rc; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int fmt = a_fmt_of(precision);
+  const bool tc = use_tc(&plan, l, precision);
+  const int pitch = tc ? l.cin_pad : l.cin;
+  if (pitch != l.cin) { free_layer(l); return fail(HG_EINVAL, "op-level entry needs C_in %% 32 == 0 on the tensor-core path"); }
+  const long long n = static_cast<long long>(B) * L * l.cin;
+  void* a = nullptr;
+  const size_t plane = align_up(static_cast<size_t>(n) * 2, 1024);
+  cudaError_t e = cudaMalloc(&a, fmt == A_F32 ? static_cast<size_t>(n) * 4 : 2 * plane);
+  if (e != cudaSuccess) { free_layer(l); return fail(HG_ECUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
+  OperandBuf in;
+  in.a0 = a;
+  in.a1 = fmt == A_BF16_SPLIT ? static_cast<uint8_t*>(a) + plane : nullptr;
+  e = launch_f32_to_operand(x, n, in_slope, fmt, in.a0, in.a1, st);
+  EpiParams ep; memset(&ep, 0, sizeof(ep));
+  ep.res = residual; ep.out_x = y; ep.slope = 1.f;
+  rc = e == cudaSuccess ? run_layer(&plan, l, precision, B, L, in, ep, st) : fail(HG_ECUDA, "f32_to_operand: %s", cudaGetErrorString(e));
+  cudaError_t es = cudaStreamSynchronize(st);
+  cudaFree(a);
+  free_layer(l);
+  if (rc) return rc;
+  if (es != cudaSuccess) return fail(HG_ECUDA, "op execution failed: %s", cudaGetErrorString(es));
+  return HG_OK;
+}
+
+extern "C" int hg_op_conv1d(int device, int precision, const float* x, int B, int L, int C_in, const float* weight,
+                            const float* bias, int C_out, int k, int dilation, float in_slope, const float* residual,
+                            float* y, void* stream) {
+  if (!x || !weight || !bias || !y) return fail(HG_EINVAL, "null argument");
+  if (B < 1 || L < 1 || C_in < 1 || C_out < 1 || k < 1 || k > kMaxTaps || dilation < 1) return fail(HG_EINVAL, "bad shape");
+  Layer l = make_conv("op.conv1d", C_in, C_out, k, dilation);
+  return op_layer(device, precision, l, x, B, L, weight, bias, in_slope, residual, y, stream);
+}
+
+extern "C" int hg_op_conv_transpose1d(int device, int precision, const float* x, int B, int L, int C_in,
+                                      const float* weight, const float* bias, int C_out, int k, int stride,
+                                      float in_slope, float* y, void* stream) {
+  if (!x || !weight || !bias || !y) return fail(HG_EINVAL, "null argument");
+  if (B < 1 || L < 1 || C_in < 1 || C_out < 1 || k < stride || stride < 1 || (k + stride - 1) / stride > kMaxTaps)
+    return fail(HG_EINVAL, "bad shape");
+  Layer l = make_convT("op.conv_transpose1d", C_in, C_out, k, stride);
+  return op_layer(device, precision, l, x, B, L, weight, bias, in_slope, nullptr, y, stream);
+}
+
+extern "C" int hg_op_conv_post(int device, const float* x, int B, int L, int C, const float* weight, const float* bias,
+                               float* y, void* stream) {
+  if (!x || !weight || !bias || !y) return fail(HG_EINVAL, "null argument");
+  int rc = check_device(device);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(device));
+  Layer l;
+  l.name = "op.conv_post"; l.kind = L_POST; l.cin = C; l.cout = 1; l.k = 7; l.pad = 3;
+  if ((rc = pack_layer(l, weight, bias))) { free_layer(l); return rc; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = launch_conv_post(x, B, L, C, l.w_post, l.bias_post, y, nullptr, 1.f, st);
+  cudaError_t es = cudaStreamSynchronize(st);
+  free_layer(l);
+  if (e != cudaSuccess) return fail(HG_ECUDA, "conv_post: %s", cudaGetErrorString(e));
+  if (es != cudaSuccess) return fail(HG_ECUDA, "conv_post execution: %s", cudaGetErrorString(es));
+  return HG_OK;
+}
+
+extern "C" int hg_selftest_tcgen05(int device, char* buf, size_t buf_len) {
+  if (buf && buf_len) buf[0] = 0;
+  int rc = check_device(device);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(device));
+  return run_tcgen05_selftest(buf, buf_len);
+}

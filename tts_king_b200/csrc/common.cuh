@@ -1,0 +1,155 @@
+// common.cuh — structures shared by the host plan and the kernels.
+//
+// Data layout in HBM (DESIGN.md "Layout"): every activation is channels-last (time-major)
+// [B][L][C].  Each stage tensor exists in up to two forms:
+//   * the fp32 residual stream x (what hifi/models.py:94 adds back), and
+//   * the "operand" copy a = leaky_relu(x) that the next convolution contracts over
+//     (hifi/models.py:90,92,188), stored in the format the arithmetic mode consumes:
+//       A_BF16        one bf16 plane                        (HG_PREC_BF16)
+//       A_BF16_SPLIT  two bf16 planes hi + lo, a ~= hi+lo    (HG_PREC_FP32, bf16x3 products)
+//       A_F32         one fp32 plane                        (HG_PREC_FP32_FFMA)
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hg {
+
+constexpr int kMaxTaps = 16;
+
+enum OperandFmt : int { A_BF16 = 0, A_BF16_SPLIT = 1, A_F32 = 2 };
+
+// Epilogue shared by every GEMM-shaped layer.  A GEMM element (item b, row q, column n) lands at
+// flat offset f = q*out_row_stride + n + out_offset inside item b's [L_out][C_out] tensor and is
+// dropped unless 0 <= f < out_extent.  For a same-length Conv1d: out_row_stride = C_out,
+// out_offset = 0.  For the polyphase ConvTranspose1d the GEMM row holds all
+// `stride` phases of one input position: out_row_stride = stride*C_out, out_offset = -pad*C_out.
+struct EpiParams {
+  const float* bias;    // [n_total]
+  const float* res;     // fp32 residual, same indexing as the output (nullable)   :94  x = xt + x
+  const float* acc_in;  // fp32 running MRF sum (nullable)                          :195 xs += ...
+  float* out_x;         // fp32 result (nullable)
+  void* out_a0;         // operand copy of leaky_relu(result): bf16 hi plane or fp32 (nullable)
+  void* out_a1;         // bf16 lo plane (A_BF16_SPLIT only)
+  int a_fmt;            // OperandFmt of out_a*
+  float slope;          // leaky_relu slope baked into the operand copy (0.1, hifi/models.py:9)
+  float post_div;       // > 0: result = (acc_in + result) / post_div                :196 xs / num_kernels
+  long long out_batch_stride;  // elements between items (= L_out*C_out)
+  long long out_offset;
+  long long out_extent;  // L_out*C_out
+  int out_row_stride;
+};
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+// Four consecutive columns n..n+3 of GEMM row q, item b (all offsets are multiples of 4 by
+// construction, so the float4 / 8-byte accesses are aligned).  `v` holds accumulator + nothing
+// yet: bias is added here.
+__device__ __forceinline__ void epilogue_vec4(const EpiParams& e, int b, long long q, int n, float v0, float v1,
+                                              float v2, float v3) {
+  const long long f = q * e.out_row_stride + n + e.out_offset;
+  if (f < 0 || f + 4 > e.out_extent) return;
+  const long long idx = static_cast<long long>(b) * e.out_batch_stride + f;
+  const float4 bb = *reinterpret_cast<const float4*>(e.bias + n);
+  v0 += bb.x; v1 += bb.y; v2 += bb.z; v3 += bb.w;
+  if (e.res) {
+    const float4 r = *reinterpret_cast<const float4*>(e.res + idx);
+    v0 += r.x; v1 += r.y; v2 += r.z; v3 += r.w;
+  }
+  if (e.acc_in) {
+    const float4 r = *reinterpret_cast<const float4*>(e.acc_in + idx);
+    v0 = r.x + v0; v1 = r.y + v1; v2 = r.z + v2; v3 = r.w + v3;
+  }
+  if (e.post_div > 0.f) {
+    v0 = __fdiv_rn(v0, e.post_div); v1 = __fdiv_rn(v1, e.post_div);
+    v2 = __fdiv_rn(v2, e.post_div); v3 = __fdiv_rn(v3, e.post_div);
+  }
+  if (e.out_x) *reinterpret_cast<float4*>(e.out_x + idx) = make_float4(v0, v1, v2, v3);
+  if (e.out_a0) {
+    const float a0 = lrelu(v0, e.slope), a1 = lrelu(v1, e.slope), a2 = lrelu(v2, e.slope), a3 = lrelu(v3, e.slope);
+    if (e.a_fmt == A_F32) {
+      *reinterpret_cast<float4*>(static_cast<float*>(e.out_a0) + idx) = make_float4(a0, a1, a2, a3);
+    } else {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
+      const __nv_bfloat16 h2 = __float2bfloat16_rn(a2), h3 = __float2bfloat16_rn(a3);
+      __nv_bfloat162 p0(h0, h1), p1(h2, h3);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&p0);
+      pk.y = *reinterpret_cast<uint32_t*>(&p1);
+      *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(e.out_a0) + idx) = pk;
+      if (e.a_fmt == A_BF16_SPLIT) {
+        __nv_bfloat162 q0(__float2bfloat16_rn(a0 - __bfloat162float(h0)), __float2bfloat16_rn(a1 - __bfloat162float(h1)));
+        __nv_bfloat162 q1(__float2bfloat16_rn(a2 - __bfloat162float(h2)), __float2bfloat16_rn(a3 - __bfloat162float(h3)));
+        uint2 pl;
+        pl.x = *reinterpret_cast<uint32_t*>(&q0);
+        pl.y = *reinterpret_cast<uint32_t*>(&q1);
+        *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(e.out_a1) + idx) = pl;
+      }
+    }
+  }
+}
+
+// Scalar variant for layers whose width is not a multiple of 4 (tiny / narrow configs on the
+// CUDA-core path).
+__device__ __forceinline__ void epilogue_scalar(const EpiParams& e, int b, long long q, int n, float v) {
+  const long long f = q * e.out_row_stride + n + e.out_offset;
+  if (f < 0 || f >= e.out_extent) return;
+  const long long idx = static_cast<long long>(b) * e.out_batch_stride + f;
+  v += e.bias[n];
+  if (e.res) v += e.res[idx];
+  if (e.acc_in) v = e.acc_in[idx] + v;
+  if (e.post_div > 0.f) v = __fdiv_rn(v, e.post_div);
+  if (e.out_x) e.out_x[idx] = v;
+  if (e.out_a0) {
+    const float a = lrelu(v, e.slope);
+    if (e.a_fmt == A_F32) {
+      static_cast<float*>(e.out_a0)[idx] = a;
+    } else {
+      const __nv_bfloat16 h = __float2bfloat16_rn(a);
+      static_cast<__nv_bfloat16*>(e.out_a0)[idx] = h;
+      if (e.a_fmt == A_BF16_SPLIT)
+        static_cast<__nv_bfloat16*>(e.out_a1)[idx] = __float2bfloat16_rn(a - __bfloat162float(h));
+    }
+  }
+}
+
+// Read one operand element in any format (CUDA-core path).
+__device__ __forceinline__ float load_operand(const void* a0, const void* a1, int fmt, long long idx) {
+  if (fmt == A_F32) return static_cast<const float*>(a0)[idx];
+  float v = __bfloat162float(static_cast<const __nv_bfloat16*>(a0)[idx]);
+  if (fmt == A_BF16_SPLIT) v += __bfloat162float(static_cast<const __nv_bfloat16*>(a1)[idx]);
+  return v;
+}
+
+// ------------------------------------------------------------------ tcgen05 implicit-GEMM conv
+struct TcConvParams {
+  int B;
+  int rows;            // GEMM rows per item (L_in for conv, L_in + 1 for the polyphase convT)
+  int tiles_per_item;  // ceil(rows / (MS*128))
+  int nc;              // K chunks of KC channels
+  int ntaps;
+  int tap_row[kMaxTaps];  // slab-relative first row of each tap (tap offset - min offset) >= 0
+  int min_off;            // slab row 0 = tile row 0 + min_off (<= 0 normally)
+  int slab_rows;          // rows per slab buffer = nboxes*box_rows
+  int box_rows, nboxes;
+  int nbuf;     // slab buffers (1 if nc == 1 else 2)
+  int stages;   // weight ring depth
+  int desc_mode;  // how a tap's row shift enters the UMMA descriptor (see conv_tc.cu)
+  const uint8_t* w_hi;  // packed swizzled weight tiles [n_blk][chunk][tap][N_T rows][KC]
+  const uint8_t* w_lo;
+  EpiParams epi;
+};
+
+// ------------------------------------------------------------------ CUDA-core (FFMA) conv
+struct FfmaConvParams {
+  int B, L_in, rows, cin, n_total;
+  int ntaps;
+  int tap_off[kMaxTaps];  // input row = q + tap_off[j]
+  const void* a0;         // operand planes, [B][L_in][cin]
+  const void* a1;
+  int a_fmt;
+  const float* w;  // [tap][cin][n_total]
+  EpiParams epi;
+};
+
+}  // namespace hg

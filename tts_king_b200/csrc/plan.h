@@ -1,0 +1,63 @@
+// plan.h — host-side plan structures of libhifigan_b200 (internal).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/hifigan_b200.h"
+#include "common.cuh"
+
+namespace hg {
+
+enum LayerKind { L_CONV = 0, L_CONVT = 1, L_POST = 2 };
+
+// One GEMM-shaped layer (or conv_post).  See conv_tc.cu for the mapping.
+struct Layer {
+  std::string name;  // state_dict prefix
+  int kind = L_CONV;
+  int cin = 0, cout = 0, k = 0, dil = 1, stride = 1, pad = 0;
+  // GEMM view
+  int ntaps = 0;
+  int tap_off[kMaxTaps] = {0};  // input row = GEMM row + tap_off
+  int n_total = 0;              // cout (conv) or stride*cout (convT)
+  // tensor-core tiling (tc == false: CUDA-core path only)
+  bool tc = false;
+  int cin_pad = 0, kc = 0, nc = 0, n_tile = 0, n_blocks = 0;
+  // device weights
+  bool loaded = false;
+  uint8_t* w_hi = nullptr;   // packed bf16 tiles (tc)
+  uint8_t* w_lo = nullptr;
+  float* w_ffma = nullptr;   // [tap][cin][n_total]
+  float* bias = nullptr;     // [n_total] (bias[n % cout]); conv_post: host scalar below
+  float* w_post = nullptr;   // conv_post: [7][C]
+  float bias_post = 0.f;
+};
+
+struct TcTiling {
+  int ms = 1, stages = 2, nbuf = 1, slab_rows = 0, box_rows = 0, nboxes = 1, min_off = 0;
+  size_t smem = 0;
+};
+
+using MapKey = std::tuple<const void*, int, int, int, int, int>;  // ptr, L, B, cpitch, kc, box_rows
+
+}  // namespace hg
+
+struct HgPlan {
+  HgConfig cfg;
+  int device = 0;
+  int sm_count = 148;
+  bool finalized = false;
+  std::vector<hg::Layer> layers;
+  std::map<std::string, int> by_name;
+  int desc_mode = 1;
+  int force_ms = 0, force_stages = 0;
+  bool force_ffma = false;  // HG_FORCE_FFMA=1: route every layer to the CUDA-core kernel
+  std::mutex mu;
+  std::map<hg::MapKey, CUtensorMap> maps;
+};

@@ -1,0 +1,154 @@
+// tail.cu — the memory-bound ends of the generator.
+//
+//   conv_post_kernel   leaky_relu(0.01) -> Conv1d(C,1,7,padding=3) -> tanh  (hifi/models.py:197-199)
+//                      optionally followed by HIFIapi.generate's  * MAX_WAV_VALUE -> int16 cast
+//                      (hifiapi.py:50-51) fused into the store.  Pure bandwidth: reads C fp32 per
+//                      sample, writes one sample (AI 3.4 FLOP/B).
+//   mel_to_operand     strided fp32 mel [B,80,T] (possibly the transpose of a time-major tensor,
+//                      tts_king.py:48) -> channels-last operand planes [B][T][C_pad] for conv_pre.
+//   f32_to_operand     fp32 channels-last -> operand planes with leaky_relu (op-level entry points).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace hg {
+
+constexpr int kPostTile = 256;  // output samples per block
+constexpr int kPostK = 7;
+
+// x: fp32 [B][L][C] raw stage output.  Block = kPostTile consecutive samples of one item.  The
+// (tile + 6) x C window is staged in shared memory with coalesced float4 loads (leaky_relu applied
+// once per element), rows padded by 4 floats so that a quarter-warp's LDS.128 hit distinct banks.
+template <bool VEC4>
+__global__ void __launch_bounds__(kPostTile) conv_post_kernel(const float* __restrict__ x, int L, int C,
+                                                              const float* __restrict__ w,  // [7][C] tap-major
+                                                              float bias, int tiles_per_item, float* __restrict__ out_f32,
+                                                              int16_t* __restrict__ out_i16, float out_scale) {
+  extern __shared__ float psm[];
+  const int pitch = VEC4 ? C + 4 : C + 1;
+  float* xs = psm;                                   // [kPostTile + 6][pitch]
+  float* ws = psm + (kPostTile + kPostK - 1) * pitch;  // [7][C]
+  const int b = blockIdx.x / tiles_per_item;
+  const int t0 = (blockIdx.x - b * tiles_per_item) * kPostTile;
+  const float* xb = x + static_cast<long long>(b) * L * C;
+  for (int e = threadIdx.x; e < kPostK * C; e += kPostTile) ws[e] = w[e];
+  if (VEC4) {
+    const int c4 = C >> 2;
+    for (int e = threadIdx.x; e < (kPostTile + kPostK - 1) * c4; e += kPostTile) {
+      const int r = e / c4, cc = (e - r * c4) << 2;
+      const int row = t0 - 3 + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row >= 0 && row < L) {
+        v = *reinterpret_cast<const float4*>(xb + static_cast<long long>(row) * C + cc);
+        v.x = lrelu(v.x, 0.01f); v.y = lrelu(v.y, 0.01f); v.z = lrelu(v.z, 0.01f); v.w = lrelu(v.w, 0.01f);
+      }
+      *reinterpret_cast<float4*>(xs + r * pitch + cc) = v;
+    }
+  } else {
+    for (int e = threadIdx.x; e < (kPostTile + kPostK - 1) * C; e += kPostTile) {
+      const int r = e / C, cc = e - r * C;
+      const int row = t0 - 3 + r;
+      xs[r * pitch + cc] = (row >= 0 && row < L) ? lrelu(xb[static_cast<long long>(row) * C + cc], 0.01f) : 0.f;
+    }
+  }
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  if (t >= L) return;
+  float acc = bias;
+#pragma unroll
+  for (int j = 0; j < kPostK; ++j) {
+    const float* xr = xs + (threadIdx.x + j) * pitch;
+    const float* wr = ws + j * C;
+    if (VEC4) {
+      for (int c = 0; c < C; c += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(xr + c);
+        const float4 ww = *reinterpret_cast<const float4*>(wr + c);
+        acc = fmaf(a.x, ww.x, acc); acc = fmaf(a.y, ww.y, acc);
+        acc = fmaf(a.z, ww.z, acc); acc = fmaf(a.w, ww.w, acc);
+      }
+    } else {
+      for (int c = 0; c < C; ++c) acc = fmaf(xr[c], wr[c], acc);
+    }
+  }
+  const float y = tanhf(acc);
+  const long long o = static_cast<long long>(b) * L + t;
+  if (out_f32) out_f32[o] = y;
+  if (out_i16) {
+    // numpy float32 -> int16: truncate toward zero to int32, keep the low 16 bits (+1.0 -> -32768)
+    const int v = __float2int_rz(y * out_scale);
+    out_i16[o] = static_cast<int16_t>(static_cast<uint16_t>(static_cast<uint32_t>(v) & 0xFFFFu));
+  }
+}
+
+cudaError_t launch_conv_post(const float* x, int B, int L, int C, const float* w_tapmajor, float bias,
+                             float* out_f32, int16_t* out_i16, float out_scale, cudaStream_t st) {
+  const int tiles = (L + kPostTile - 1) / kPostTile;
+  const bool vec = (C & 3) == 0;
+  const int pitch = vec ? C + 4 : C + 1;
+  const size_t smem = (static_cast<size_t>(kPostTile + kPostK - 1) * pitch + kPostK * C) * sizeof(float);
+  dim3 grid(static_cast<unsigned>(B * tiles));
+  if (vec) {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(conv_post_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    conv_post_kernel<true><<<grid, kPostTile, smem, st>>>(x, L, C, w_tapmajor, bias, tiles, out_f32, out_i16, out_scale);
+  } else {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(conv_post_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    conv_post_kernel<false><<<grid, kPostTile, smem, st>>>(x, L, C, w_tapmajor, bias, tiles, out_f32, out_i16, out_scale);
+  }
+  return cudaGetLastError();
+}
+
+// mel [B, C, T] with element strides (sB, sC, sT)  ->  operand planes [B][T][c_pad], zero padded.
+__global__ void mel_to_operand_kernel(const float* __restrict__ mel, long long sB, long long sC, long long sT, int B,
+                                      int C, int T, int c_pad, int a_fmt, void* __restrict__ a0, void* __restrict__ a1) {
+  const long long total = static_cast<long long>(B) * T * c_pad;
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(e % c_pad);
+    const long long bt = e / c_pad;
+    const int t = static_cast<int>(bt % T);
+    const int b = static_cast<int>(bt / T);
+    const float v = c < C ? mel[b * sB + c * sC + t * sT] : 0.f;
+    if (a_fmt == A_F32) {
+      static_cast<float*>(a0)[e] = v;
+    } else {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      static_cast<__nv_bfloat16*>(a0)[e] = h;
+      if (a_fmt == A_BF16_SPLIT) static_cast<__nv_bfloat16*>(a1)[e] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+
+cudaError_t launch_mel_to_operand(const float* mel, long long sB, long long sC, long long sT, int B, int C, int T,
+                                  int c_pad, int a_fmt, void* a0, void* a1, cudaStream_t st) {
+  const long long total = static_cast<long long>(B) * T * c_pad;
+  const int blocks = static_cast<int>((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  mel_to_operand_kernel<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(mel, sB, sC, sT, B, C, T, c_pad, a_fmt, a0, a1);
+  return cudaGetLastError();
+}
+
+// x fp32 [n] -> operand planes of leaky_relu(x, slope)  (slope 1.0 = identity)
+__global__ void f32_to_operand_kernel(const float* __restrict__ x, long long n, float slope, int a_fmt,
+                                      void* __restrict__ a0, void* __restrict__ a1) {
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < n;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float v = lrelu(x[e], slope);
+    if (a_fmt == A_F32) {
+      static_cast<float*>(a0)[e] = v;
+    } else {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      static_cast<__nv_bfloat16*>(a0)[e] = h;
+      if (a_fmt == A_BF16_SPLIT) static_cast<__nv_bfloat16*>(a1)[e] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+
+cudaError_t launch_f32_to_operand(const float* x, long long n, float slope, int a_fmt, void* a0, void* a1,
+                                  cudaStream_t st) {
+  const int blocks = static_cast<int>((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
+  f32_to_operand_kernel<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(x, n, slope, a_fmt, a0, a1);
+  return cudaGetLastError();
+}
+
+}  // namespace hg

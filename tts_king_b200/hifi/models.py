@@ -1,0 +1,322 @@
+"""HiFi-GAN generator with the reference's Python surface and a CUDA engine underneath.
+
+Mirror of the inference half of the reference's ``hifi/models.py`` (``Generator`` :146-210,
+``ResBlock1`` :12-101, ``ResBlock2`` :104-143): same constructor, same module tree and therefore the
+same ``state_dict`` keys (``weight_g`` / ``weight_v`` / ``bias`` before ``remove_weight_norm``,
+``weight`` / ``bias`` after), same ``forward(mel[B,80,T]) -> wav[B,1,T*prod(rates)]``.
+
+What differs is everything below that surface.  The ``torch.nn`` modules are parameter containers
+only; ``forward`` folds the weight norm, hands the tensors to ``libhifigan_b200.so`` (C ABI in
+``include/hifigan_b200.h``) and runs the whole network as ~80 hand-written sm_100a kernels
+(tcgen05 implicit-GEMM convolutions with fused bias / leaky-ReLU / residual / MRF epilogues).
+Inference only: the output never requires grad.  CUDA only: a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+from torch.nn import Conv1d, ConvTranspose1d
+from torch.nn.utils import remove_weight_norm, weight_norm
+
+from .. import _native
+from .vocoder.utils import get_padding, init_weights
+
+LRELU_SLOPE = 0.1
+NUM_MELS = 80  # the reference hard-codes Conv1d(80, ...) at hifi/models.py:153
+
+
+def _wn_conv(channels: int, kernel_size: int, dilation: int) -> nn.Module:
+    return weight_norm(Conv1d(channels, channels, kernel_size, 1, dilation=dilation,
+                              padding=get_padding(kernel_size, dilation)))
+
+
+def _folded(m: nn.Module) -> torch.Tensor:
+    """The effective weight of a (possibly still weight-normed) conv: torch._weight_norm(v, g, 0) —
+    exactly what remove_weight_norm bakes in (reference hifi/models.py:97-101,203-210)."""
+    if hasattr(m, "weight_g"):
+        return torch._weight_norm(m.weight_v.detach(), m.weight_g.detach(), 0)
+    return m.weight.detach()
+
+
+def _run_op_conv(m: Conv1d, x_cl: torch.Tensor, in_slope: float, residual: Optional[torch.Tensor],
+                 precision: str) -> torch.Tensor:
+    """One Conv1d through the op-level C entry point; x_cl is channels-last [B, L, C] on CUDA."""
+    L = _native.lib()
+    w = _folded(m).float().cpu().contiguous()
+    b = m.bias.detach().float().cpu().contiguous()
+    B, n, cin = x_cl.shape
+    y = torch.empty((B, n, m.out_channels), dtype=torch.float32, device=x_cl.device)
+    with torch.cuda.device(x_cl.device):
+        st = torch.cuda.current_stream().cuda_stream
+        _native.check(L.hg_op_conv1d(x_cl.device.index, _native.PRECISIONS[precision], x_cl.data_ptr(), B, n, cin,
+                                     w.data_ptr(), b.data_ptr(), m.out_channels, m.kernel_size[0], m.dilation[0],
+                                     float(in_slope), residual.data_ptr() if residual is not None else None,
+                                     y.data_ptr(), st))
+    return y
+
+
+class _ResBlockBase(nn.Module):
+    precision = "fp32"
+
+    def _check(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError("tts_king_b200 ResBlock runs only on CUDA (sm_100a); there is no CPU fallback")
+        return x.detach().float().transpose(1, 2).contiguous()  # [B, L, C]
+
+
+class ResBlock1(_ResBlockBase):
+    """Three (dilated conv, conv) pairs with pre-activation residuals — reference hifi/models.py:12-101."""
+
+    def __init__(self, h, channels, kernel_size=3, dilation=(1, 3, 5)):
+        super().__init__()
+        self.h = h
+        self.convs1 = nn.ModuleList([_wn_conv(channels, kernel_size, dilation[m]) for m in range(3)])
+        self.convs1.apply(init_weights)
+        self.convs2 = nn.ModuleList([_wn_conv(channels, kernel_size, 1) for _ in range(3)])
+        self.convs2.apply(init_weights)
+
+    def forward(self, x):
+        # stand-alone use (block-level parity tests); Generator.forward runs the fused schedule
+        r = self._check(x)
+        for c1, c2 in zip(self.convs1, self.convs2):
+            xt = _run_op_conv(c1, r, LRELU_SLOPE, None, self.precision)
+            r = _run_op_conv(c2, xt, LRELU_SLOPE, r, self.precision)
+        return r.transpose(1, 2).contiguous()
+
+    def remove_weight_norm(self):
+        for m in list(self.convs1) + list(self.convs2):
+            remove_weight_norm(m)
+
+
+class ResBlock2(_ResBlockBase):
+    """Two dilated convs with pre-activation residuals — reference hifi/models.py:104-143."""
+
+    def __init__(self, h, channels, kernel_size=3, dilation=(1, 3)):
+        super().__init__()
+        self.h = h
+        self.convs = nn.ModuleList([_wn_conv(channels, kernel_size, dilation[m]) for m in range(2)])
+        self.convs.apply(init_weights)
+
+    def forward(self, x):
+        r = self._check(x)
+        for c in self.convs:
+            r = _run_op_conv(c, r, LRELU_SLOPE, r, self.precision)
+        return r.transpose(1, 2).contiguous()
+
+    def remove_weight_norm(self):
+        for m in self.convs:
+            remove_weight_norm(m)
+
+
+class _Engine:
+    """Owns one HgPlan (device weights in kernel layout) and the scratch workspaces."""
+
+    def __init__(self, cfg: _native.HgConfig, device: torch.device, weights: List[Tuple[str, torch.Tensor, torch.Tensor]]):
+        self.L = _native.lib()
+        self.device = device
+        self.plan = ctypes.c_void_p()
+        _native.check(self.L.hg_plan_create(ctypes.byref(cfg), device.index, ctypes.byref(self.plan)))
+        try:
+            for name, w, b in weights:
+                shape = (ctypes.c_int64 * w.dim())(*w.shape)
+                _native.check(self.L.hg_plan_upload_weight(self.plan, name.encode(), w.data_ptr(), shape, w.dim(),
+                                                           b.data_ptr(), b.numel()))
+            _native.check(self.L.hg_plan_finalize(self.plan))
+        except Exception:
+            self.close()
+            raise
+        self._ws: Dict[int, torch.Tensor] = {}
+
+    def close(self):
+        if self.plan:
+            self.L.hg_plan_destroy(self.plan)
+            self.plan = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def workspace(self, B: int, T: int, prec: int, stream: int) -> Tuple[int, int]:
+        need = ctypes.c_size_t()
+        _native.check(self.L.hg_workspace_bytes(self.plan, B, T, prec, ctypes.byref(need)))
+        buf = self._ws.get(stream)
+        if buf is None or buf.numel() < need.value + 1024:
+            self._ws.pop(stream, None)
+            buf = None
+            buf = torch.empty(need.value + 1024, dtype=torch.uint8, device=self.device)
+            self._ws[stream] = buf
+        base = (buf.data_ptr() + 1023) & ~1023
+        return base, buf.numel() - (base - buf.data_ptr())
+
+    def launches(self, B: int, T: int, prec: int) -> int:
+        n = ctypes.c_int()
+        _native.check(self.L.hg_forward_launches(self.plan, B, T, prec, ctypes.byref(n)))
+        return n.value
+
+    def forward(self, mel: torch.Tensor, out: torch.Tensor, out_dtype: int, out_scale: float, prec: int):
+        B, _, T = mel.shape
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream().cuda_stream
+            ws, ws_bytes = self.workspace(B, T, prec, st)
+            sB, sC, sT = mel.stride()
+            _native.check(self.L.hg_forward(self.plan, mel.data_ptr(), sB, sC, sT, B, T, out.data_ptr(), out_dtype,
+                                            float(out_scale), prec, ws, ws_bytes, st))
+
+
+class Generator(nn.Module):
+    """``Generator(h)`` — reference hifi/models.py:146-210.
+
+    ``h`` needs the attributes the reference reads: ``resblock`` ("1" or "2"), ``upsample_rates``,
+    ``upsample_kernel_sizes``, ``upsample_initial_channel``, ``resblock_kernel_sizes``,
+    ``resblock_dilation_sizes``.
+
+    ``precision`` (attribute, not part of the reference API) selects the arithmetic of the
+    contraction: ``"fp32"`` (default; bf16x3 split products on tensor cores, fp32-accurate),
+    ``"bf16"`` (bf16 operands, fp32 accumulate and residual stream) or ``"fp32_ffma"`` (exact fp32
+    on CUDA cores, slow).
+    """
+
+    def __init__(self, h, precision: str = "fp32"):
+        super().__init__()
+        self.h = h
+        self.num_kernels = len(h.resblock_kernel_sizes)
+        self.num_upsamples = len(h.upsample_rates)
+        uic = h.upsample_initial_channel
+        self.conv_pre = weight_norm(Conv1d(NUM_MELS, uic, 7, 1, padding=3))
+        block = ResBlock1 if h.resblock == "1" else ResBlock2
+
+        self.ups = nn.ModuleList()
+        for i, (u, k) in enumerate(zip(h.upsample_rates, h.upsample_kernel_sizes)):
+            self.ups.append(weight_norm(ConvTranspose1d(uic // (2 ** i), uic // (2 ** (i + 1)), k, u,
+                                                        padding=(k - u) // 2)))
+
+        self.resblocks = nn.ModuleList()
+        ch = uic
+        for i in range(len(self.ups)):
+            ch = uic // (2 ** (i + 1))
+            for k, d in zip(h.resblock_kernel_sizes, h.resblock_dilation_sizes):
+                self.resblocks.append(block(h, ch, k, d))
+
+        self.conv_post = weight_norm(Conv1d(ch, 1, 7, 1, padding=3))
+        self.ups.apply(init_weights)
+        self.conv_post.apply(init_weights)
+
+        if precision not in _native.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_native.PRECISIONS)}")
+        self.precision = precision
+        self._engine: Optional[_Engine] = None
+        self._engine_key = None
+
+    # ------------------------------------------------------------------ reference API
+    def remove_weight_norm(self):
+        print("Removing weight norm for inference HIFI GAN...")
+        for m in self.ups:
+            remove_weight_norm(m)
+        for blk in self.resblocks:
+            blk.remove_weight_norm()
+        remove_weight_norm(self.conv_pre)
+        remove_weight_norm(self.conv_post)
+
+    def forward(self, x):
+        return self._run(x, _native.OUT_F32, 1.0)
+
+    # ------------------------------------------------------------------ extensions
+    @torch.no_grad()
+    def generate_int16(self, x, max_wav_value: float = 32768.0):
+        """forward + ``* MAX_WAV_VALUE`` + numpy-style truncating int16 cast, fused into the last
+        kernel (the tail of reference hifiapi.py:47-51).  Returns a device int16 tensor [B,1,N]."""
+        return self._run(x, _native.OUT_I16, float(max_wav_value))
+
+    @property
+    def hop_length(self) -> int:
+        n = 1
+        for u in self.h.upsample_rates:
+            n *= int(u)
+        return n
+
+    def kernel_launches(self, B: int, T: int) -> int:
+        """Kernels one forward enqueues (bench.py reports it as gpu_launches)."""
+        eng = self._get_engine()
+        return eng.launches(B, T, _native.PRECISIONS[self.precision])
+
+    # ------------------------------------------------------------------ internals
+    def __getstate__(self):
+        # the native plan is process-local: drop it on pickle / deepcopy, it is rebuilt on demand
+        state = self.__dict__.copy()
+        state["_engine"] = None
+        state["_engine_key"] = None
+        return state
+
+    def _convs(self) -> List[Tuple[str, nn.Module]]:
+        out: List[Tuple[str, nn.Module]] = [("conv_pre", self.conv_pre)]
+        out += [(f"ups.{i}", m) for i, m in enumerate(self.ups)]
+        for n, blk in enumerate(self.resblocks):
+            if isinstance(blk, ResBlock1):
+                out += [(f"resblocks.{n}.convs1.{m}", c) for m, c in enumerate(blk.convs1)]
+                out += [(f"resblocks.{n}.convs2.{m}", c) for m, c in enumerate(blk.convs2)]
+            else:
+                out += [(f"resblocks.{n}.convs.{m}", c) for m, c in enumerate(blk.convs)]
+        out.append(("conv_post", self.conv_post))
+        return out
+
+    def _native_config(self) -> _native.HgConfig:
+        h = self.h
+        c = _native.HgConfig()
+        c.num_mels = NUM_MELS
+        c.upsample_initial_channel = int(h.upsample_initial_channel)
+        c.num_upsamples = self.num_upsamples
+        for i, (u, k) in enumerate(zip(h.upsample_rates, h.upsample_kernel_sizes)):
+            c.upsample_rates[i] = int(u)
+            c.upsample_kernel_sizes[i] = int(k)
+        c.num_kernels = self.num_kernels
+        rb1 = h.resblock == "1"
+        for j, (k, ds) in enumerate(zip(h.resblock_kernel_sizes, h.resblock_dilation_sizes)):
+            c.resblock_kernel_sizes[j] = int(k)
+            for m in range(3 if rb1 else 2):
+                c.resblock_dilation_sizes[j][m] = int(ds[m])
+        c.resblock_type = 1 if rb1 else 2
+        return c
+
+    def _get_engine(self) -> _Engine:
+        params = list(self.parameters())
+        device = params[0].device
+        if device.type != "cuda":
+            raise RuntimeError(
+                "tts_king_b200.Generator runs only on a CUDA sm_100a device; move the module with .to('cuda') "
+                "(there is no CPU fallback)")
+        key = (device, tuple((p.data_ptr(), p._version) for p in params))
+        if self._engine is None or self._engine_key != key:
+            if self._engine is not None:
+                self._engine.close()
+            weights = [(name, _folded(m).float().cpu().contiguous(), m.bias.detach().float().cpu().contiguous())
+                       for name, m in self._convs()]
+            self._engine = _Engine(self._native_config(), device, weights)
+            self._engine_key = key
+        return self._engine
+
+    def _run(self, x, out_dtype: int, out_scale: float):
+        if not isinstance(x, torch.Tensor):
+            raise TypeError("expected a Tensor")
+        squeeze = x.dim() == 2
+        if squeeze:
+            x = x.unsqueeze(0)
+        if x.dim() != 3 or x.shape[1] != NUM_MELS:
+            raise RuntimeError(f"expected input[B, {NUM_MELS}, T] (or [{NUM_MELS}, T]), got {list(x.shape)}")
+        eng = self._get_engine()
+        if x.device != eng.device:
+            raise RuntimeError(f"input is on {x.device} but the generator's weights are on {eng.device}")
+        if x.shape[0] == 0 or x.shape[2] == 0:
+            raise RuntimeError("empty batch / zero-length mel")
+        x = x.detach()
+        if x.dtype != torch.float32:
+            x = x.float()
+        B, _, T = x.shape
+        out = torch.empty((B, 1, T * self.hop_length), device=x.device,
+                          dtype=torch.float32 if out_dtype == _native.OUT_F32 else torch.int16)
+        eng.forward(x, out, out_dtype, out_scale, _native.PRECISIONS[self.precision])
+        return out.squeeze(0) if squeeze else out
