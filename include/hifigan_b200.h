@@ -148,6 +148,27 @@ HG_API int hg_op_conv_post(int device, const float* x, int B, int L, int C, cons
                     const float* bias, float* y, void* stream);
 
 /*
+ * Per-layer timing (bench.py's roofline pass; the reference has no profiler).
+ * hg_layer_count / hg_layer_info describe the plan's layer table; hg_profile_forward runs one
+ * hg_forward with CUDA events recorded on `stream` around every launch and, after synchronizing,
+ * returns for launch i the plan layer it ran (layer_index[i], -1 = the mel repack) and its device
+ * time in milliseconds.
+ */
+typedef struct HgLayerInfo {
+  char name[64];     /* state_dict prefix */
+  int32_t kind;      /* 0 Conv1d, 1 ConvTranspose1d, 2 conv_post(+tanh) */
+  int32_t c_in, c_out, k, dilation, stride;
+  int32_t tensor_core; /* 1: tcgen05 path available for this layer */
+  int32_t n_tile, k_chunk, m_subtiles, stages, smem_bytes; /* tcgen05 tiling at `precision` */
+} HgLayerInfo;
+HG_API int hg_layer_count(const HgPlan* plan, int* count);
+HG_API int hg_layer_info(const HgPlan* plan, int index, int precision, HgLayerInfo* info);
+HG_API int hg_profile_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC, int64_t sT, int B,
+                              int T, void* out, int out_dtype, float out_scale, int precision,
+                              void* workspace, size_t workspace_bytes, void* stream,
+                              int* layer_index, float* layer_ms, int max_launches, int* n_launches);
+
+/*
  * Debug / bring-up: runs the tcgen05 descriptor self-test (shifted-row UMMA descriptors against a
  * CUDA-core reference) and writes a report into `buf`.  Returns the number of failing cases.
  */

@@ -1,0 +1,182 @@
+"""T3-T7 — end-to-end parity of the CUDA generator against the reference's own outputs
+(tests/golden/, produced by tools/make_golden.py from /root/reference) and against the CPU oracle.
+Needs a B200: run with `-m gpu` under gpurun.
+
+Tolerances are the north_star's: fp32 path max-abs <= 1e-4, bf16 path SNR >= 40 dB.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fixtures as fx
+from oracle import torch_oracle
+from oracle.common import ac_snr_db, max_abs, snr_db
+from tts_king_b200 import parallel
+
+from _util import golden, make_generator, stored_state
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4      # north_star: fp32 max-abs error <= 1e-4
+BF16_SNR_DB = 40.0   # north_star: bf16 path SNR >= 40 dB against the fp32 reference
+FULL = [("v1", fx.V1), ("v2_narrow", fx.V2_NARROW), ("v3_rb2", fx.V3_RB2)]
+
+
+def gpu_forward(m, mel):
+    with torch.no_grad():
+        y = m(mel.cuda())
+    torch.cuda.synchronize()
+    return y.cpu()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp32_ffma"])
+@pytest.mark.parametrize("name,cfg", FULL)
+def test_fp32_paths_match_reference(name, cfg, prec):
+    """T3: same random-init weights (seed 1234, digest-checked), same synthetic mels."""
+    g = golden(name + "_seed1234")
+    m = make_generator(cfg, precision=prec)
+    assert fx.state_digest(m.state_dict()) == str(g["digest_folded"])
+    m.cuda()
+    ya = gpu_forward(m, torch.from_numpy(g["mel_a"]))
+    assert ya.shape == g["y_a"].shape
+    assert max_abs(ya.numpy(), g["y_a"]) <= FP32_TOL
+    # ragged batch of log-mel-like values, passed as the non-contiguous transpose of a time-major
+    # tensor exactly as tts_king.py:48 does
+    mel_b = torch.from_numpy(g["mel_b"]).transpose(1, 2).contiguous().cuda().transpose(1, 2)
+    assert not mel_b.is_contiguous()
+    yb = gpu_forward(m, mel_b)
+    assert max_abs(yb.numpy(), g["y_b"]) <= FP32_TOL
+
+
+@pytest.mark.parametrize("name,cfg", FULL)
+def test_fp32_alive_weights(name, cfg):
+    """T3b: trained-like gains expose rounding that the attenuating default init hides
+    (single-pass TF32 fails here)."""
+    g = golden(name + "_seed1234")
+    m = make_generator(cfg, precision="fp32")
+    m.load_state_dict(fx.alive_state(cfg))
+    m.cuda()
+    y = gpu_forward(m, torch.from_numpy(g["mel_a"]))
+    assert max_abs(y.numpy(), g["y_alive_a"]) <= FP32_TOL
+
+
+@pytest.mark.parametrize("name,cfg", FULL)
+def test_bf16_snr(name, cfg):
+    """T4: bf16 operands, fp32 accumulate + residual stream."""
+    g = golden(name + "_seed1234")
+    m = make_generator(cfg, precision="bf16").cuda()
+    y = gpu_forward(m, torch.from_numpy(g["mel_a"])).numpy()
+    assert snr_db(g["y_a"], y) >= BF16_SNR_DB, (snr_db(g["y_a"], y), ac_snr_db(g["y_a"], y))
+    m.load_state_dict(fx.alive_state(cfg))
+    ya = gpu_forward(m, torch.from_numpy(g["mel_a"])).numpy()
+    assert snr_db(g["y_alive_a"], ya) >= BF16_SNR_DB, snr_db(g["y_alive_a"], ya)
+
+
+@pytest.mark.parametrize("name,cfg", [("tiny_rb1", fx.TINY_RB1), ("tiny_rb2", fx.TINY_RB2)])
+def test_stored_weights_and_edge_shapes(name, cfg):
+    """T5: load_state_dict of a reference-produced g/v state_dict; T = 1; unbatched input."""
+    g = golden(name)
+    m = make_generator(cfg, seed=5, fold=False)
+    m.load_state_dict(stored_state(g))
+    m.cuda()
+    y = gpu_forward(m, torch.from_numpy(g["mel"]))
+    assert max_abs(y.numpy(), g["y"]) <= FP32_TOL
+    y1 = gpu_forward(m, torch.from_numpy(g["mel_T1"]))
+    assert y1.shape == g["y_T1"].shape and max_abs(y1.numpy(), g["y_T1"]) <= FP32_TOL
+    yu = gpu_forward(m, torch.from_numpy(g["mel"][0]))  # [80,T] -> [1,T*hop]
+    assert yu.shape == (1, g["y"].shape[-1]) and max_abs(yu.numpy(), g["y"][0]) <= FP32_TOL
+    # folded-layout load and the int16 tail of HIFIapi.generate on a full-scale signal
+    mf = make_generator(cfg, seed=6, fold=True)
+    mf.load_state_dict(stored_state(g, "alive."))
+    mf.cuda()
+    ya = gpu_forward(mf, torch.from_numpy(g["mel"]))
+    assert max_abs(ya.numpy(), g["y_alive"]) <= FP32_TOL
+    i16 = mf.generate_int16(torch.from_numpy(g["mel"]).cuda()).cpu().numpy()
+    assert i16.dtype == np.int16 and i16.shape == g["y_alive_int16"].shape
+    assert np.abs(i16.astype(np.int32) - g["y_alive_int16"].astype(np.int32)).max() <= 4  # 1e-4 * 32768 = 3.3 LSB
+
+
+def test_wrong_channel_count_raises():
+    m = make_generator(fx.TINY_RB1).cuda()
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 79, 5, device="cuda"))
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 80, 5))  # CPU tensor into a CUDA module
+
+
+def test_hifiapi_drop_in():
+    """T5: the wrapper end to end — generate() int16 and __call__ float against the reference's."""
+    from tts_king_b200.hifiapi import AttrDict, HIFIapi
+
+    g = golden("hifiapi_v1")
+    cfg = AttrDict(hifi=fx.make_h(fx.V1), model_config=AttrDict(vocoder=AttrDict(use_cpu=True)))
+    cfg.hifi["weights_path"] = None
+    torch.manual_seed(1234)
+    api = HIFIapi(cfg, "cpu")
+    mel = torch.from_numpy(g["mel"])
+    wav = api.generate(mel)
+    assert isinstance(wav, np.ndarray) and wav.dtype == np.int16 and wav.shape == g["generate_int16"].shape
+    assert np.abs(wav.astype(np.int32) - g["generate_int16"].astype(np.int32)).max() <= 4
+    y = api(mel)
+    assert y.device.type == "cpu" and max_abs(y.numpy(), g["call_f32"]) <= FP32_TOL
+
+
+def test_checkpoint_file_roundtrip(tmp_path):
+    """hifiapi.py:20-22: torch.load(path)["generator"] in the g/v layout."""
+    from tts_king_b200.hifiapi import AttrDict, HIFIapi
+
+    g = golden("tiny_rb1")
+    path = str(tmp_path / "hifi.pth")
+    torch.save({"generator": stored_state(g)}, path)
+    cfg = AttrDict(hifi=fx.make_h(fx.TINY_RB1), model_config=AttrDict(vocoder=AttrDict(use_cpu=False)))
+    cfg.hifi["weights_path"] = path
+    api = HIFIapi(cfg, "cuda")
+    y = api(torch.from_numpy(g["mel"]))
+    assert y.is_cuda and max_abs(y.cpu().numpy(), g["y"]) <= FP32_TOL
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_chunked_equals_full_on_gpu(prec):
+    """T6: 13-frame halo chunking reproduces the monolithic forward."""
+    m = make_generator(fx.V1, precision=prec).cuda()
+    h = fx.make_h(fx.V1)
+    halo, hop = parallel.halo_frames(h), parallel.hop_length(h)
+    mel = fx.synthetic_mel(1, 150, seed=9).cuda()
+    with torch.no_grad():
+        full = m(mel)
+        y = parallel.chunked_forward(m, mel, 40, halo, hop)
+    assert y.shape == full.shape
+    assert max_abs(y.cpu().numpy(), full.cpu().numpy()) <= 1e-6
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_batch_items_are_independent(prec):
+    """T7: utterance sharding is exact — an item's result does not depend on its batch."""
+    m = make_generator(fx.V1, precision=prec).cuda()
+    mel = fx.synthetic_mel(3, 64, seed=21).cuda()
+    with torch.no_grad():
+        yb = m(mel)
+        ys = torch.cat([m(mel[i:i + 1]) for i in range(3)], dim=0)
+    assert torch.equal(yb, ys)
+
+
+def test_full_size_cross_check_against_ffma():
+    """BASELINE cfg-2 scale (16 x 800 frames): the tensor-core fp32 path against the exact-fp32
+    CUDA-core path on the device (the CPU oracle would take minutes), plus bf16 SNR."""
+    mel = fx.synthetic_mel(16, 800, seed=7).cuda()
+    m = make_generator(fx.V1, precision="fp32_ffma").cuda()
+    with torch.no_grad():
+        ref = m(mel).cpu().numpy()
+        m.precision = "fp32"
+        y32 = m(mel).cpu().numpy()
+        m.precision = "bf16"
+        y16 = m(mel).cpu().numpy()
+    assert max_abs(y32, ref) <= FP32_TOL
+    assert snr_db(ref, y16) >= BF16_SNR_DB
+    # one utterance of that batch against the CPU oracle (the reference's arithmetic)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    cpu = torch_oracle.forward(fx.V1, sd, mel[3:4, :, :200].cpu())
+    with torch.no_grad():
+        m.precision = "fp32"
+        part = m(mel[3:4, :, :200]).cpu()
+    assert max_abs(part.numpy(), cpu.numpy()) <= FP32_TOL

@@ -1,0 +1,174 @@
+"""T1/T2 — op- and block-level parity of the CUDA kernels (through the C ABI) against fp64
+torch.nn.functional on the host.  Needs a B200: run with `-m gpu` under gpurun."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tts_king_b200 import _native
+
+pytestmark = pytest.mark.gpu
+
+PREC = {"fp32": 1, "bf16": 0, "fp32_ffma": 2}
+
+
+def bf16_round(t):
+    return t.float().bfloat16().double()
+
+
+def split_round(t):
+    hi = t.float().bfloat16().float()
+    lo = (t.float() - hi).bfloat16().float()
+    return (hi + lo).double()
+
+
+def operand_model(t, prec):
+    """What the kernel contracts over, given fp32 values: exact, bf16, or hi+lo."""
+    return {"fp32_ffma": t.double(), "bf16": bf16_round(t), "fp32": split_round(t)}[prec]
+
+
+def run_conv1d(x, w, b, d, slope, res, prec):
+    """x [B,C,L] cpu float -> y [B,Cout,L] via hg_op_conv1d (channels-last on device)."""
+    L = _native.lib()
+    dev = torch.device("cuda", 0)
+    xc = x.transpose(1, 2).contiguous().to(dev)
+    rc = res.transpose(1, 2).contiguous().to(dev) if res is not None else None
+    B, n, cin = xc.shape
+    cout, _, k = w.shape
+    y = torch.full((B, n, cout), float("nan"), device=dev)
+    wc, bc = w.contiguous(), b.contiguous()
+    _native.check(L.hg_op_conv1d(0, PREC[prec], xc.data_ptr(), B, n, cin, wc.data_ptr(), bc.data_ptr(), cout, k, d,
+                                 float(slope), rc.data_ptr() if rc is not None else None, y.data_ptr(),
+                                 torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    return y.cpu().transpose(1, 2)
+
+
+def ref_conv1d(x, w, b, d, slope, res, prec):
+    a = operand_model(F.leaky_relu(x, slope) if slope != 1.0 else x, prec)
+    ww = operand_model(w, prec) if prec != "fp32" else split_round(w)
+    k = w.shape[-1]
+    y = F.conv1d(a, ww, b.double(), dilation=d, padding=(k * d - d) // 2)
+    return y + res.double() if res is not None else y
+
+
+TOL = {"fp32_ffma": 2e-6, "fp32": 3e-5, "bf16": 3e-5}  # relative to max|y|, vs the operand model
+
+
+@pytest.mark.parametrize("prec", ["fp32_ffma", "fp32", "bf16"])
+@pytest.mark.parametrize("C,k,d", [(256, 3, 1), (256, 11, 5), (128, 7, 3), (128, 11, 1), (64, 3, 5), (64, 11, 5),
+                                   (32, 3, 1), (32, 7, 3), (32, 11, 5)])
+def test_conv1d_parity(C, k, d, prec):
+    g = torch.Generator().manual_seed(C * 100 + k * 10 + d)
+    B, n = 2, 301  # odd length: ragged last tile, and shorter than one 2x128-row CTA tile pair
+    x = torch.randn(B, C, n, generator=g)
+    w = torch.randn(C, C, k, generator=g) / (C * k) ** 0.5
+    b = torch.randn(C, generator=g) * 0.1
+    res = torch.randn(B, C, n, generator=g)
+    y = run_conv1d(x, w, b, d, 0.1, res, prec)
+    ref = ref_conv1d(x, w, b, d, 0.1, res, prec)
+    err = (y.double() - ref).abs().max().item()
+    assert not torch.isnan(y).any()
+    assert err <= TOL[prec] * ref.abs().max().item(), (err, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("n", [1, 2, 127, 128, 129, 255, 256, 257, 1000])
+def test_conv1d_lengths(n, prec):
+    """Tile-boundary lengths and T = 1."""
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(3, 64, n, generator=g)
+    w = torch.randn(64, 64, 7, generator=g) / 21.0
+    b = torch.randn(64, generator=g)
+    y = run_conv1d(x, w, b, 3, 0.1, None, prec)
+    ref = ref_conv1d(x, w, b, 3, 0.1, None, prec)
+    assert (y.double() - ref).abs().max().item() <= TOL[prec] * max(1.0, ref.abs().max().item())
+
+
+def test_conv1d_fp32_mode_is_fp32_accurate():
+    """HG_PREC_FP32 (bf16x3) against the true fp64 result of the fp32 inputs — the accuracy the
+    north_star's 1e-4 end-to-end bound rests on."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 128, 500, generator=g)
+    w = torch.randn(128, 128, 11, generator=g) / (128 * 11) ** 0.5
+    b = torch.zeros(128)
+    y = run_conv1d(x, w, b, 5, 1.0, None, "fp32")
+    ref = F.conv1d(x.double(), w.double(), None, dilation=5, padding=25)
+    rel = (y.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert rel <= 5e-5, rel
+
+
+@pytest.mark.parametrize("prec", ["fp32_ffma", "fp32", "bf16"])
+@pytest.mark.parametrize("cin,cout,k,s", [(512, 256, 16, 8), (256, 128, 16, 8), (128, 64, 4, 2), (64, 32, 4, 2),
+                                          (256, 128, 8, 4)])
+def test_conv_transpose1d_parity(cin, cout, k, s, prec):
+    L = _native.lib()
+    g = torch.Generator().manual_seed(cin + k)
+    B, n = 2, 37
+    x = torch.randn(B, cin, n, generator=g)
+    w = torch.randn(cin, cout, k, generator=g) / (cin * k / s) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    dev = torch.device("cuda", 0)
+    xc = x.transpose(1, 2).contiguous().to(dev)
+    y = torch.full((B, n * s, cout), float("nan"), device=dev)
+    _native.check(L.hg_op_conv_transpose1d(0, PREC[prec], xc.data_ptr(), B, n, cin, w.data_ptr(), b.data_ptr(), cout, k,
+                                           s, 0.1, y.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    y = y.cpu().transpose(1, 2)
+    a = operand_model(F.leaky_relu(x, 0.1), prec)
+    ww = operand_model(w, prec)
+    ref = F.conv_transpose1d(a, ww, b.double(), stride=s, padding=(k - s) // 2)
+    assert not torch.isnan(y).any()
+    assert (y.double() - ref).abs().max().item() <= TOL[prec] * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("C", [32, 8, 2])
+def test_conv_post_parity(C):
+    L = _native.lib()
+    g = torch.Generator().manual_seed(C)
+    B, n = 3, 777
+    x = torch.randn(B, C, n, generator=g)
+    w = torch.randn(1, C, 7, generator=g) / (7 * C) ** 0.5
+    b = torch.randn(1, generator=g)
+    dev = torch.device("cuda", 0)
+    xc = x.transpose(1, 2).contiguous().to(dev)
+    y = torch.full((B, n), float("nan"), device=dev)
+    _native.check(L.hg_op_conv_post(0, xc.data_ptr(), B, n, C, w.data_ptr(), b.data_ptr(), y.data_ptr(),
+                                    torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = torch.tanh(F.conv1d(F.leaky_relu(x.double(), 0.01), w.double(), b.double(), padding=3))[:, 0]
+    assert (y.cpu().double() - ref).abs().max().item() <= 2e-6
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_resblock1_block_level(prec):
+    """T2: ResBlock1(C,k,(1,3,5)) stand-alone against the fp64 restatement of hifi/models.py:88-95."""
+    from oracle import fixtures as fx
+    from tts_king_b200.hifi.models import ResBlock1
+
+    torch.manual_seed(3)
+    blk = ResBlock1(fx.make_h(fx.V1), 128, 7, (1, 3, 5))
+    blk.precision = prec
+    x = torch.randn(2, 128, 333)
+    y = blk.cuda()(x.cuda()).cpu()
+    r = x.double()
+    for c1, c2 in zip(blk.convs1, blk.convs2):
+        w1 = torch._weight_norm(c1.weight_v, c1.weight_g, 0).detach().cpu().double()
+        w2 = torch._weight_norm(c2.weight_v, c2.weight_g, 0).detach().cpu().double()
+        xt = F.conv1d(F.leaky_relu(r, 0.1), w1, c1.bias.detach().cpu().double(), dilation=c1.dilation[0], padding=c1.padding[0])
+        xt = F.conv1d(F.leaky_relu(xt, 0.1), w2, c2.bias.detach().cpu().double(), padding=c2.padding[0])
+        r = xt + r
+    err = (y.double() - r).abs().max().item()
+    assert err <= (2e-5 if prec == "fp32" else 5e-2) * r.abs().max().item(), err
+
+
+def test_tcgen05_descriptor_selftest():
+    n, report = _native.selftest(0)
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    open("gpurun_out/selftest_tcgen05.txt", "w").write(report)
+    mode = int(os.environ.get("HG_DESC_MODE", "1"))
+    bad = [ln for ln in report.splitlines() if f"mode={mode} " in ln and "MISMATCH" in ln]
+    assert not bad, "\n".join(bad)

@@ -359,6 +359,23 @@ extern "C" int hg_plan_destroy(HgPlan* plan) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// optional per-launch event recording (hg_profile_forward)
+struct ProfSink {
+  cudaStream_t st;
+  std::vector<cudaEvent_t> ev;   // ev[0] = before the first launch, ev[i+1] = after launch i
+  std::vector<int> layer;        // plan layer index per launch (-1 = mel repack)
+};
+static thread_local ProfSink* g_prof = nullptr;
+static void prof_mark(int layer_index) {
+  if (!g_prof) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, g_prof->st);
+  g_prof->ev.push_back(e);
+  if (layer_index > -2) g_prof->layer.push_back(layer_index);
+}
+
+// ------------------------------------------------------------------------------------------------
 // launching one GEMM-shaped layer
 struct OperandBuf {
   void* a0 = nullptr;
@@ -444,6 +461,7 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
       if (split && (rc = make_operand_map(plan, in.a1, L_in, B, l.cin_pad, l.kc, t.box_rows, &ml))) return rc;
       cudaError_t e = launch_conv_tc(l.n_tile, l.kc, t.ms, split, mh, ml, p, l.n_blocks, t.smem, st);
       if (e != cudaSuccess) return fail(HG_ECUDA, "conv_tc launch (%s): %s", l.name.c_str(), cudaGetErrorString(e));
+      if (g_prof) prof_mark(static_cast<int>(&l - plan->layers.data()));
       return HG_OK;
     }
   }
@@ -456,6 +474,7 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
   if (l.cin_pad != l.cin) return fail(HG_ESTATE, "internal: padded operand on the CUDA-core path (%s)", l.name.c_str());
   cudaError_t e = launch_conv_ffma(f, st);
   if (e != cudaSuccess) return fail(HG_ECUDA, "conv_ffma launch (%s): %s", l.name.c_str(), cudaGetErrorString(e));
+  if (g_prof) prof_mark(static_cast<int>(&l - plan->layers.data()));
   return HG_OK;
 }
 
@@ -557,10 +576,12 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
   const int U = c.num_upsamples, K = c.num_kernels, D = rb_dilations(c);
   const float slope = 0.1f;  // LRELU_SLOPE, hifi/models.py:9
 
+  prof_mark(-2);
   // mel [B,80,T] (any strides) -> channels-last operand
   cudaError_t e = launch_mel_to_operand(mel, sB, sC, sT, B, c.num_mels, T, mel_pitch(plan, precision), fmt, ws.mel.a0,
                                         ws.mel.a1, st);
   if (e != cudaSuccess) return fail(HG_ECUDA, "mel_to_operand: %s", cudaGetErrorString(e));
+  prof_mark(-1);
 
   // x = conv_pre(x)  :186 ; only leaky_relu(x) is consumed (by ups[0], :188-189)
   int a_cur = 1;  // operand buffer holding leaky_relu(current x)
@@ -634,6 +655,61 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
                        out_dtype == HG_OUT_F32 ? static_cast<float*>(out) : nullptr,
                        out_dtype == HG_OUT_I16 ? static_cast<int16_t*>(out) : nullptr, out_scale, st);
   if (e != cudaSuccess) return fail(HG_ECUDA, "conv_post: %s", cudaGetErrorString(e));
+  prof_mark(static_cast<int>(plan->layers.size()) - 1);
+  return HG_OK;
+}
+
+extern "C" int hg_layer_count(const HgPlan* plan, int* count) {
+  if (!plan || !count) return fail(HG_EINVAL, "null argument");
+  *count = static_cast<int>(plan->layers.size());
+  return HG_OK;
+}
+
+extern "C" int hg_layer_info(const HgPlan* plan, int index, int precision, HgLayerInfo* info) {
+  if (!plan || !info) return fail(HG_EINVAL, "null argument");
+  if (index < 0 || index >= static_cast<int>(plan->layers.size())) return fail(HG_EINVAL, "layer index out of range");
+  if (precision < HG_PREC_BF16 || precision > HG_PREC_FP32_FFMA) return fail(HG_EINVAL, "unknown precision");
+  const Layer& l = plan->layers[index];
+  memset(info, 0, sizeof(*info));
+  snprintf(info->name, sizeof(info->name), "%s", l.name.c_str());
+  info->kind = l.kind; info->c_in = l.cin; info->c_out = l.cout; info->k = l.k;
+  info->dilation = l.dil; info->stride = l.stride;
+  info->tensor_core = use_tc(plan, l, precision) ? 1 : 0;
+  if (info->tensor_core) {
+    TcTiling t = choose_tiling(plan, l, precision == HG_PREC_FP32);
+    info->tensor_core = t.stages >= 2 ? 1 : 0;
+    info->n_tile = l.n_tile; info->k_chunk = l.kc; info->m_subtiles = t.ms; info->stages = t.stages;
+    info->smem_bytes = static_cast<int32_t>(t.smem);
+  }
+  return HG_OK;
+}
+
+extern "C" int hg_profile_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC, int64_t sT, int B, int T,
+                                  void* out, int out_dtype, float out_scale, int precision, void* workspace,
+                                  size_t workspace_bytes, void* stream, int* layer_index, float* layer_ms,
+                                  int max_launches, int* n_launches) {
+  if (!layer_index || !layer_ms || !n_launches) return fail(HG_EINVAL, "null argument");
+  ProfSink sink;
+  sink.st = static_cast<cudaStream_t>(stream);
+  g_prof = &sink;
+  int rc = hg_forward(plan, mel, sB, sC, sT, B, T, out, out_dtype, out_scale, precision, workspace, workspace_bytes, stream);
+  g_prof = nullptr;
+  cudaError_t es = cudaStreamSynchronize(sink.st);
+  int n = 0;
+  if (!rc && es == cudaSuccess) {
+    n = static_cast<int>(sink.layer.size());
+    if (n > max_launches) n = max_launches;
+    for (int i = 0; i < n; ++i) {
+      layer_index[i] = sink.layer[i];
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, sink.ev[i], sink.ev[i + 1]);
+      layer_ms[i] = ms;
+    }
+  }
+  for (cudaEvent_t e : sink.ev) cudaEventDestroy(e);
+  if (rc) return rc;
+  if (es != cudaSuccess) return fail(HG_ECUDA, "profile_forward: %s", cudaGetErrorString(es));
+  *n_launches = n;
   return HG_OK;
 }
 

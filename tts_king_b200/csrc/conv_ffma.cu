@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(const FfmaConvParams p, 
       __syncthreads();
     }
   }
-  const bool vec = (p.n_total & 3) == 0;
+  // float4 epilogue only when every flat offset it produces is a multiple of 4
+  const bool vec = ((static_cast<long long>(p.n_total) | p.epi.out_offset | p.epi.out_extent) & 3) == 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const long long q = static_cast<long long>(m0) + ty * 4 + i;

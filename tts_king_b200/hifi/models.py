@@ -168,6 +168,33 @@ class _Engine:
                                             float(out_scale), prec, ws, ws_bytes, st))
 
 
+    def layer_table(self, prec: int) -> List[_native.HgLayerInfo]:
+        n = ctypes.c_int()
+        _native.check(self.L.hg_layer_count(self.plan, ctypes.byref(n)))
+        out = []
+        for i in range(n.value):
+            info = _native.HgLayerInfo()
+            _native.check(self.L.hg_layer_info(self.plan, i, prec, ctypes.byref(info)))
+            out.append(info)
+        return out
+
+    def profile(self, mel: torch.Tensor, out: torch.Tensor, prec: int) -> List[Tuple[int, float]]:
+        """One forward with CUDA events around every launch: [(plan layer index | -1, ms), ...]."""
+        B, _, T = mel.shape
+        cap = 4096
+        idx = (ctypes.c_int * cap)()
+        ms = (ctypes.c_float * cap)()
+        n = ctypes.c_int()
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream().cuda_stream
+            ws, ws_bytes = self.workspace(B, T, prec, st)
+            sB, sC, sT = mel.stride()
+            _native.check(self.L.hg_profile_forward(self.plan, mel.data_ptr(), sB, sC, sT, B, T, out.data_ptr(),
+                                                    _native.OUT_F32, 1.0, prec, ws, ws_bytes, st, idx, ms, cap,
+                                                    ctypes.byref(n)))
+        return [(idx[i], ms[i]) for i in range(n.value)]
+
+
 class Generator(nn.Module):
     """``Generator(h)`` — reference hifi/models.py:146-210.
 
@@ -243,6 +270,26 @@ class Generator(nn.Module):
         """Kernels one forward enqueues (bench.py reports it as gpu_launches)."""
         eng = self._get_engine()
         return eng.launches(B, T, _native.PRECISIONS[self.precision])
+
+    @torch.no_grad()
+    def profile_layers(self, x):
+        """Per-launch device times of one forward: list of dicts (name, kind, shape, tiling, ms)."""
+        eng = self._get_engine()
+        prec = _native.PRECISIONS[self.precision]
+        x = x.detach().float()
+        B, _, T = x.shape
+        out = torch.empty((B, 1, T * self.hop_length), device=x.device, dtype=torch.float32)
+        table = eng.layer_table(prec)
+        rows = []
+        for li, ms in eng.profile(x, out, prec):
+            if li < 0:
+                rows.append(dict(name="mel_to_operand", kind=-1, ms=ms))
+                continue
+            t = table[li]
+            rows.append(dict(name=t.name.decode(), kind=t.kind, c_in=t.c_in, c_out=t.c_out, k=t.k, dilation=t.dilation,
+                             stride=t.stride, tensor_core=bool(t.tensor_core), n_tile=t.n_tile, k_chunk=t.k_chunk,
+                             m_subtiles=t.m_subtiles, stages=t.stages, smem_bytes=t.smem_bytes, ms=ms))
+        return rows
 
     # ------------------------------------------------------------------ internals
     def __getstate__(self):
