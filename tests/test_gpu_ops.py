@@ -169,6 +169,6 @@ def test_tcgen05_descriptor_selftest():
     import os
     os.makedirs("gpurun_out", exist_ok=True)
     open("gpurun_out/selftest_tcgen05.txt", "w").write(report)
-    mode = int(os.environ.get("HG_DESC_MODE", "1"))
+    mode = int(os.environ.get("HG_DESC_MODE", "0"))
     bad = [ln for ln in report.splitlines() if f"mode={mode} " in ln and "MISMATCH" in ln]
     assert not bad, "\n".join(bad)

@@ -193,7 +193,7 @@ extern "C" int hg_plan_create(const HgConfig* cfg, int device, HgPlan** out) {
   p->device = device;
   cudaDeviceProp pr;
   if (cudaGetDeviceProperties(&pr, device) == cudaSuccess) p->sm_count = pr.multiProcessorCount;
-  p->desc_mode = env_int("HG_DESC_MODE", 1);
+  p->desc_mode = env_int("HG_DESC_MODE", 0);
   p->force_ms = env_int("HG_TC_MS", 0);
   p->force_stages = env_int("HG_TC_STAGES", 0);
   p->force_ffma = env_int("HG_FORCE_FFMA", 0) != 0;
@@ -467,11 +467,11 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
   }
   FfmaConvParams f;
   memset(&f, 0, sizeof(f));
-  f.B = B; f.L_in = L_in; f.rows = rows; f.cin = l.cin_pad; f.n_total = l.n_total; f.ntaps = l.ntaps;
+  f.B = B; f.L_in = L_in; f.rows = rows; f.cin = l.cin; f.n_total = l.n_total; f.ntaps = l.ntaps;
+  f.a_pitch = use_tc(plan, l, precision) ? l.cin_pad : l.cin;  // matches mel_pitch() for conv_pre
   for (int j = 0; j < l.ntaps; ++j) f.tap_off[j] = l.tap_off[j];
   f.a0 = in.a0; f.a1 = in.a1; f.a_fmt = a_fmt_of(precision);
   f.w = l.w_ffma; f.epi = epi;
-  if (l.cin_pad != l.cin) return fail(HG_ESTATE, "internal: padded operand on the CUDA-core path (%s)", l.name.c_str());
   cudaError_t e = launch_conv_ffma(f, st);
   if (e != cudaSuccess) return fail(HG_ECUDA, "conv_ffma launch (%s): %s", l.name.c_str(), cudaGetErrorString(e));
   if (g_prof) prof_mark(static_cast<int>(&l - plan->layers.data()));
@@ -723,7 +723,7 @@ static int op_layer(int device, int precision, Layer& l, const float* x, int B, 
   CUDA_TRY(cudaSetDevice(device));
   HgPlan plan;
   plan.device = device;
-  plan.desc_mode = env_int("HG_DESC_MODE", 1);
+  plan.desc_mode = env_int("HG_DESC_MODE", 0);
   plan.force_ms = env_int("HG_TC_MS", 0);
   plan.force_stages = env_int("HG_TC_STAGES", 0);
   plan.force_ffma = env_int("HG_FORCE_FFMA", 0) != 0;

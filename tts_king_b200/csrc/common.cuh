@@ -145,7 +145,8 @@ struct FfmaConvParams {
   int B, L_in, rows, cin, n_total;
   int ntaps;
   int tap_off[kMaxTaps];  // input row = q + tap_off[j]
-  const void* a0;         // operand planes, [B][L_in][cin]
+  int a_pitch;            // channels per operand row (>= cin when the producer padded)
+  const void* a0;         // operand planes, [B][L_in][a_pitch]
   const void* a1;
   int a_fmt;
   const float* w;  // [tap][cin][n_total]

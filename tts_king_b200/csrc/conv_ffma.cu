@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(const FfmaConvParams p, 
       const int row = m0 + min_off + r, c = c0 + kk;
       float v = 0.f;
       if (row >= 0 && row < p.L_in && c < p.cin)
-        v = load_operand(p.a0, p.a1, p.a_fmt, (static_cast<long long>(b) * p.L_in + row) * p.cin + c);
+        v = load_operand(p.a0, p.a1, p.a_fmt, (static_cast<long long>(b) * p.L_in + row) * p.a_pitch + c);
       slab[r * (FT_K + 1) + kk] = v;
     }
     for (int t = 0; t < p.ntaps; ++t) {

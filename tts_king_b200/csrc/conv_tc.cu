@@ -34,8 +34,10 @@ struct SwzOf {
 };
 
 __device__ __forceinline__ uint32_t desc_base_offset(uint32_t saddr, int desc_mode) {
-  // desc_mode 0: swizzle phase taken from absolute address bits, base_offset stays 0.
-  // desc_mode 1: base_offset = (start address >> 7) & 7 (PTX ISA matrix-descriptor formula).
+  // desc_mode 0 (default, verified on B200 by hg_selftest_tcgen05 for every row shift, SW128 and
+  //   SW64): the XOR swizzle phase comes from absolute smem address bits, base_offset stays 0.
+  // desc_mode 1: base_offset = (start address >> 7) & 7 — measured WRONG for shifts that are not a
+  //   multiple of 8 rows; kept only so the self-test can document it.
   return desc_mode == 1 ? ((saddr >> 7) & 7u) : 0u;
 }
 

@@ -55,7 +55,7 @@ struct HgPlan {
   bool finalized = false;
   std::vector<hg::Layer> layers;
   std::map<std::string, int> by_name;
-  int desc_mode = 1;
+  int desc_mode = 0;  // measured on B200 (selftest.cu): UMMA swizzle phase comes from absolute smem address bits
   int force_ms = 0, force_stages = 0;
   bool force_ffma = false;  // HG_FORCE_FFMA=1: route every layer to the CUDA-core kernel
   std::mutex mu;
