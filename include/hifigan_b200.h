@@ -160,6 +160,7 @@ typedef struct HgLayerInfo {
   int32_t c_in, c_out, k, dilation, stride;
   int32_t tensor_core; /* 1: tcgen05 path available for this layer */
   int32_t n_tile, k_chunk, m_subtiles, stages, smem_bytes; /* tcgen05 tiling at `precision` */
+  int32_t weights_resident, slab_buffers;
 } HgLayerInfo;
 HG_API int hg_layer_count(const HgPlan* plan, int* count);
 HG_API int hg_layer_info(const HgPlan* plan, int index, int precision, HgLayerInfo* info);

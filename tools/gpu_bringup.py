@@ -134,7 +134,7 @@ def g_perf():
                 print(f"  {r['name']:28s} {r['ms']:.3f} ms")
                 continue
             print(f"  {r['name']:28s} {r['c_in']:4d}->{r['c_out']:4d} k={r['k']:2d} d={r['dilation']} s={r['stride']} "
-                  f"tc={int(r['tensor_core'])} nt={r['n_tile']} ms={r['m_subtiles']} st={r['stages']} smem={r['smem_bytes']} "
+                  f"tc={int(r['tensor_core'])} nt={r['n_tile']} ms={r['m_subtiles']} st={r['stages']} res={int(r['weights_resident'])} nb={r['slab_buffers']} smem={r['smem_bytes']} "
                   f"{r['ms']:.3f} ms")
         json.dump(rows, open(os.path.join(OUT, f"layers_{prec}.json"), "w"))
 

@@ -35,7 +35,7 @@ class HgConfig(ctypes.Structure):
 class HgLayerInfo(ctypes.Structure):
     _fields_ = [("name", ctypes.c_char * 64)] + [(n, ctypes.c_int32) for n in (
         "kind", "c_in", "c_out", "k", "dilation", "stride", "tensor_core", "n_tile", "k_chunk", "m_subtiles",
-        "stages", "smem_bytes")]
+        "stages", "smem_bytes", "weights_resident", "slab_buffers")]
 
 
 class NativeError(RuntimeError):

@@ -17,7 +17,7 @@ namespace hg {
 // kernels.cu-side launchers
 size_t conv_tc_smem_bytes(int n_t, int kc, bool split, int slab_rows, int nbuf, int stages);
 cudaError_t launch_conv_tc(int n_t, int kc, int ms, bool split, const CUtensorMap& mh, const CUtensorMap& ml,
-                           const TcConvParams& p, int n_blocks, size_t smem, cudaStream_t st);
+                           const TcConvParams& p, int n_blocks, size_t smem, int grid_ctas, cudaStream_t st);
 cudaError_t launch_conv_ffma(const FfmaConvParams& p, cudaStream_t st);
 cudaError_t launch_conv_post(const float* x, int B, int L, int C, const float* w_tapmajor, float bias, float* out_f32,
                              int16_t* out_i16, float out_scale, cudaStream_t st);
@@ -197,6 +197,7 @@ extern "C" int hg_plan_create(const HgConfig* cfg, int device, HgPlan** out) {
   p->force_ms = env_int("HG_TC_MS", 0);
   p->force_stages = env_int("HG_TC_STAGES", 0);
   p->force_ffma = env_int("HG_FORCE_FFMA", 0) != 0;
+  p->ctas_per_sm = env_int("HG_TC_CTAS_PER_SM", 1);
   const int uic = cfg->upsample_initial_channel;
   p->layers.push_back(make_conv("conv_pre", cfg->num_mels, uic, 7, 1));
   for (int i = 0; i < cfg->num_upsamples; ++i) {
@@ -399,32 +400,40 @@ static TcTiling choose_tiling(const HgPlan* plan, const Layer& l, bool split) {
   }
   t.min_off = min_off;
   const int span = max_off - min_off;
+  // two accumulator buffers of MS x N_T fp32 columns must fit the 512 TMEM columns
   int ms = l.n_tile == 256 ? 1 : l.n_tile == 128 ? 2 : l.n_tile == 64 ? 2 : 4;
   if (plan->force_ms) ms = plan->force_ms;
-  while (ms * l.n_tile > 512) ms >>= 1;
+  while (2 * ms * l.n_tile > 512) ms >>= 1;
   const size_t kMaxSmem = 227 * 1024;
+  const int total_stages = l.nc * l.ntaps * (split ? 2 : 1);
   for (;; ms >>= 1) {
     t.ms = ms;
     const int need = ms * 128 + span;
     t.nboxes = (need + 255) / 256;
     t.box_rows = (((need + t.nboxes - 1) / t.nboxes) + 7) / 8 * 8;
     t.slab_rows = t.nboxes * t.box_rows;
-    t.nbuf = l.nc > 1 ? 2 : 1;
-    const int total_stages = l.nc * l.ntaps * (split ? 2 : 1);
-    // weight ring: as deep as fits next to the slab while leaving room for a second resident CTA
-    // when that still gives >= 3 stages; otherwise use the whole SM.
-    int best = 0;
-    for (int target : {static_cast<int>(kMaxSmem / 2) - 1024, static_cast<int>(kMaxSmem)}) {
-      int s = 8;
-      while (s >= 2 && conv_tc_smem_bytes(l.n_tile, l.kc, split, t.slab_rows, t.nbuf, s) > static_cast<size_t>(target)) --s;
-      if (s >= 3 || (target == static_cast<int>(kMaxSmem) && s >= 2)) { best = s; break; }
-    }
-    if (plan->force_stages) best = plan->force_stages;
-    if (best >= 2 && conv_tc_smem_bytes(l.n_tile, l.kc, split, t.slab_rows, t.nbuf, best) <= kMaxSmem) {
-      t.stages = std::min(best, std::max(2, total_stages));
+    t.stages = 0;
+    // 1) weights resident for the CTA's lifetime (single N block only) with a double-buffered slab
+    if (l.n_blocks == 1 && !plan->force_stages &&
+        conv_tc_smem_bytes(l.n_tile, l.kc, split, t.slab_rows, 2, total_stages) <= kMaxSmem) {
+      t.resident = true;
+      t.stages = total_stages;
+      t.nbuf = 2;
+      if (conv_tc_smem_bytes(l.n_tile, l.kc, split, t.slab_rows, 3, total_stages) <= kMaxSmem) t.nbuf = 3;
       break;
     }
-    if (ms == 1) { t.stages = 0; break; }  // does not fit at all
+    // 2) weights streamed through a ring: at least 3 stages next to a double-buffered slab
+    t.resident = false;
+    t.nbuf = 2;
+    int s = 8;
+    while (s >= 2 && conv_tc_smem_bytes(l.n_tile, l.kc, split, t.slab_rows, t.nbuf, s) > kMaxSmem) --s;
+    if (plan->force_stages) s = plan->force_stages;
+    if (s >= 2 && conv_tc_smem_bytes(l.n_tile, l.kc, split, t.slab_rows, t.nbuf, s) <= kMaxSmem) {
+      t.stages = s;
+      if (s >= 4 && conv_tc_smem_bytes(l.n_tile, l.kc, split, t.slab_rows, 3, s) <= kMaxSmem) t.nbuf = 3;
+      break;
+    }
+    if (ms == 1) break;  // does not fit at all -> CUDA-core path
   }
   t.smem = conv_tc_smem_bytes(l.n_tile, l.kc, split, t.slab_rows, t.nbuf, t.stages);
   return t;
@@ -453,13 +462,17 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
       for (int j = 0; j < l.ntaps; ++j) p.tap_row[j] = l.tap_off[j] - t.min_off;
       p.min_off = t.min_off; p.slab_rows = t.slab_rows; p.box_rows = t.box_rows; p.nboxes = t.nboxes;
       p.nbuf = t.nbuf; p.stages = t.stages; p.desc_mode = plan->desc_mode;
+      p.w_resident = t.resident ? 1 : 0;
+      p.n_blocks = l.n_blocks;
+      p.total_work = B * p.tiles_per_item * l.n_blocks;
       p.w_hi = l.w_hi; p.w_lo = l.w_lo; p.epi = epi;
       CUtensorMap mh, ml;
       int rc = make_operand_map(plan, in.a0, L_in, B, l.cin_pad, l.kc, t.box_rows, &mh);
       if (rc) return rc;
       ml = mh;
       if (split && (rc = make_operand_map(plan, in.a1, L_in, B, l.cin_pad, l.kc, t.box_rows, &ml))) return rc;
-      cudaError_t e = launch_conv_tc(l.n_tile, l.kc, t.ms, split, mh, ml, p, l.n_blocks, t.smem, st);
+      const int grid = std::min(p.total_work, plan->sm_count * std::max(1, plan->ctas_per_sm));
+      cudaError_t e = launch_conv_tc(l.n_tile, l.kc, t.ms, split, mh, ml, p, l.n_blocks, t.smem, grid, st);
       if (e != cudaSuccess) return fail(HG_ECUDA, "conv_tc launch (%s): %s", l.name.c_str(), cudaGetErrorString(e));
       if (g_prof) prof_mark(static_cast<int>(&l - plan->layers.data()));
       return HG_OK;
@@ -680,6 +693,7 @@ extern "C" int hg_layer_info(const HgPlan* plan, int index, int precision, HgLay
     info->tensor_core = t.stages >= 2 ? 1 : 0;
     info->n_tile = l.n_tile; info->k_chunk = l.kc; info->m_subtiles = t.ms; info->stages = t.stages;
     info->smem_bytes = static_cast<int32_t>(t.smem);
+    info->weights_resident = t.resident ? 1 : 0; info->slab_buffers = t.nbuf;
   }
   return HG_OK;
 }
@@ -727,6 +741,11 @@ static int op_layer(int device, int precision, Layer& l, const float* x, int B, 
   plan.force_ms = env_int("HG_TC_MS", 0);
   plan.force_stages = env_int("HG_TC_STAGES", 0);
   plan.force_ffma = env_int("HG_FORCE_FFMA", 0) != 0;
+  plan.ctas_per_sm = env_int("HG_TC_CTAS_PER_SM", 1);
+  {
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, device) == cudaSuccess) plan.sm_count = pr.multiProcessorCount;
+  }
   if ((rc = pack_layer(l, weight, bias))) { free_layer(l); return rc; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int fmt = a_fmt_of(precision);

@@ -89,6 +89,104 @@ __device__ __forceinline__ void epilogue_vec4(const EpiParams& e, int b, long lo
   }
 }
 
+// NR rows (q0, q0+row_step, ...) x four columns per thread with every global load issued before the
+// first use — the memory-level parallelism the HBM-bound layers live on.  Same arithmetic and
+// ordering as epilogue_vec4; index math is one 64-bit base plus a constant step.
+__device__ __forceinline__ uint2 pack_bf16x4(float a0, float a1, float a2, float a3) {
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(a0, a1), p1 = __floats2bfloat162_rn(a2, a3);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&p0);
+  pk.y = *reinterpret_cast<uint32_t*>(&p1);
+  return pk;
+}
+// leaky_relu for 0 <= slope <= 1 in two instructions
+__device__ __forceinline__ float lrelu_fast(float v, float slope) { return fmaxf(v, v * slope); }
+
+template <int NR>
+__device__ __forceinline__ void epilogue_rows(const EpiParams& e, int b, long long q0, int row_step, int n,
+                                              float (&v)[NR][4]) {
+  const long long f0 = q0 * e.out_row_stride + n + e.out_offset;
+  const long long fstep = static_cast<long long>(row_step) * e.out_row_stride;
+  const long long base = static_cast<long long>(b) * e.out_batch_stride;
+  bool ok[NR];
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    const long long f = f0 + i * fstep;
+    ok[i] = f >= 0 && f + 4 <= e.out_extent;
+  }
+  const float4 bb = *reinterpret_cast<const float4*>(e.bias + n);
+  if (e.res) {
+    const float* rp = e.res + base + f0;
+    float4 r[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) r[i] = ok[i] ? *reinterpret_cast<const float4*>(rp + i * fstep) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      v[i][0] = (v[i][0] + bb.x) + r[i].x; v[i][1] = (v[i][1] + bb.y) + r[i].y;
+      v[i][2] = (v[i][2] + bb.z) + r[i].z; v[i][3] = (v[i][3] + bb.w) + r[i].w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NR; ++i) { v[i][0] += bb.x; v[i][1] += bb.y; v[i][2] += bb.z; v[i][3] += bb.w; }
+  }
+  if (e.acc_in) {
+    const float* ap = e.acc_in + base + f0;
+    float4 r[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) r[i] = ok[i] ? *reinterpret_cast<const float4*>(ap + i * fstep) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      v[i][0] = r[i].x + v[i][0]; v[i][1] = r[i].y + v[i][1]; v[i][2] = r[i].z + v[i][2]; v[i][3] = r[i].w + v[i][3];
+    }
+  }
+  if (e.post_div > 0.f) {
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      v[i][0] = __fdiv_rn(v[i][0], e.post_div); v[i][1] = __fdiv_rn(v[i][1], e.post_div);
+      v[i][2] = __fdiv_rn(v[i][2], e.post_div); v[i][3] = __fdiv_rn(v[i][3], e.post_div);
+    }
+  }
+  if (e.out_x) {
+    float* xp = e.out_x + base + f0;
+#pragma unroll
+    for (int i = 0; i < NR; ++i)
+      if (ok[i]) *reinterpret_cast<float4*>(xp + i * fstep) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+  }
+  if (e.out_a0) {
+    const float sl = e.slope;
+    if (e.a_fmt == A_BF16) {
+      __nv_bfloat16* hp = static_cast<__nv_bfloat16*>(e.out_a0) + base + f0;
+#pragma unroll
+      for (int i = 0; i < NR; ++i)
+        if (ok[i])
+          *reinterpret_cast<uint2*>(hp + i * fstep) = pack_bf16x4(lrelu_fast(v[i][0], sl), lrelu_fast(v[i][1], sl),
+                                                                  lrelu_fast(v[i][2], sl), lrelu_fast(v[i][3], sl));
+    } else if (e.a_fmt == A_BF16_SPLIT) {
+      __nv_bfloat16* hp = static_cast<__nv_bfloat16*>(e.out_a0) + base + f0;
+      __nv_bfloat16* lp = static_cast<__nv_bfloat16*>(e.out_a1) + base + f0;
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        if (!ok[i]) continue;
+        const float a0 = lrelu_fast(v[i][0], sl), a1 = lrelu_fast(v[i][1], sl), a2 = lrelu_fast(v[i][2], sl), a3 = lrelu_fast(v[i][3], sl);
+        const __nv_bfloat162 h01 = __floats2bfloat162_rn(a0, a1), h23 = __floats2bfloat162_rn(a2, a3);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+        pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+        *reinterpret_cast<uint2*>(hp + i * fstep) = pk;
+        *reinterpret_cast<uint2*>(lp + i * fstep) =
+            pack_bf16x4(a0 - __low2float(h01), a1 - __high2float(h01), a2 - __low2float(h23), a3 - __high2float(h23));
+      }
+    } else {
+      float* fp = static_cast<float*>(e.out_a0) + base + f0;
+#pragma unroll
+      for (int i = 0; i < NR; ++i)
+        if (ok[i])
+          *reinterpret_cast<float4*>(fp + i * fstep) = make_float4(lrelu_fast(v[i][0], sl), lrelu_fast(v[i][1], sl),
+                                                                   lrelu_fast(v[i][2], sl), lrelu_fast(v[i][3], sl));
+    }
+  }
+}
+
 // Scalar variant for layers whose width is not a multiple of 4 (tiny / narrow configs on the
 // CUDA-core path).
 __device__ __forceinline__ void epilogue_scalar(const EpiParams& e, int b, long long q, int n, float v) {
@@ -132,8 +230,11 @@ struct TcConvParams {
   int min_off;            // slab row 0 = tile row 0 + min_off (<= 0 normally)
   int slab_rows;          // rows per slab buffer = nboxes*box_rows
   int box_rows, nboxes;
-  int nbuf;     // slab buffers (1 if nc == 1 else 2)
-  int stages;   // weight ring depth
+  int nbuf;     // slab chunk ring depth
+  int stages;   // weight ring depth (== nc*ntaps*planes when w_resident)
+  int w_resident;  // 1: every weight tile stays in shared memory for the CTA's lifetime
+  int n_blocks;    // N tiles (grid-strided together with the M tiles)
+  int total_work;  // B * tiles_per_item * n_blocks
   int desc_mode;  // how a tap's row shift enters the UMMA descriptor (see conv_tc.cu)
   const uint8_t* w_hi;  // packed swizzled weight tiles [n_blk][chunk][tap][N_T rows][KC]
   const uint8_t* w_lo;

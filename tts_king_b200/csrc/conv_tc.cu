@@ -15,8 +15,8 @@
 // Weights are pre-packed on the host into swizzled [N_T x KC] tiles and streamed through a ring of
 // stages with 1-D bulk copies.  Accumulators (MS sub-tiles of 128 rows) live in TMEM.
 //
-// Warp roles (224 threads): 0 weight producer | 1 MMA issuer + TMEM owner | 2 slab producer |
-// 3..6 epilogue (TMEM lane quarter = warp % 4).
+// Warp roles (608 threads): 0 weight producer | 1 MMA issuer + TMEM owner | 2 slab producer |
+// 3..18 epilogue (TMEM lane quarter = warp % 4; four warps per quarter split the column chunks).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdio.h>
@@ -26,7 +26,9 @@
 
 namespace hg {
 
-constexpr int kTcThreads = 224;
+constexpr int kEpiWarps = 16;
+constexpr int kTcThreads = (3 + kEpiWarps) * 32;  // 608
+constexpr int kStageFloats = 32 * 16;            // per-warp transpose tile: 32 rows x 16 fp32 columns
 
 template <int KC>
 struct SwzOf {
@@ -41,6 +43,10 @@ __device__ __forceinline__ uint32_t desc_base_offset(uint32_t saddr, int desc_mo
   return desc_mode == 1 ? ((saddr >> 7) & 7u) : 0u;
 }
 
+// Persistent: grid = min(work items, SMs); every role walks the same grid-strided list of work
+// items (item -> batch item b, M tile, N block).  Accumulators are double-buffered in TMEM so the
+// epilogue of item i overlaps the MMAs of item i+1; the slab and weight rings run ahead across
+// item boundaries.
 template <int N_T, int KC, int MS, bool SPLIT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
@@ -49,8 +55,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   constexpr int PLANES = SPLIT ? 2 : 1;
   constexpr int STAGE_BYTES = N_T * ROWB;
   constexpr int KSTEPS = KC / 16;              // UMMA K = 16 bf16
-  constexpr uint32_t TMEM_COLS = MS * N_T;     // fp32 accumulator columns
+  constexpr uint32_t ACC_COLS = MS * N_T;      // fp32 accumulator columns per buffer
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
   constexpr uint32_t SBO = 8 * ROWB;           // bytes between 8-row groups
+  constexpr int CHUNKS = N_T / 16;             // 16-column epilogue chunks per sub-tile
   static_assert(TMEM_COLS >= 32 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns");
 
   extern __shared__ uint8_t smem_raw[];
@@ -58,21 +66,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   const int slab_bytes = p.slab_rows * ROWB;
   uint8_t* slab = smem;
   uint8_t* wst = smem + ((p.nbuf * PLANES * slab_bytes + 1023) & ~1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wst + p.stages * STAGE_BYTES);
-  uint64_t* slab_full = bars;          // [2]
-  uint64_t* slab_empty = bars + 2;     // [2]
-  uint64_t* acc_full = bars + 4;       // [1]
-  uint64_t* w_full = bars + 5;         // [stages]
+  float* staging = reinterpret_cast<float*>(wst + p.stages * STAGE_BYTES);  // [kEpiWarps][32*16]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kEpiWarps * kStageFloats);
+  uint64_t* slab_full = bars;           // [4]
+  uint64_t* slab_empty = bars + 4;      // [4]
+  uint64_t* acc_full = bars + 8;        // [2]
+  uint64_t* acc_empty = bars + 10;      // [2]
+  uint64_t* w_full = bars + 12;         // [stages]
   uint64_t* w_empty = w_full + p.stages;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_empty + p.stages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x / p.tiles_per_item;
-  const int tile = blockIdx.x - b * p.tiles_per_item;
-  const int m0 = tile * (MS * 128);
-  const int nblk = blockIdx.y;
-  int ms_count = (p.rows - m0 + 127) / 128;
-  ms_count = ms_count > MS ? MS : ms_count;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&map_hi);
@@ -80,9 +84,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   }
   if (warp == 1) {
     if (lane == 0) {
-      mbar_init(&slab_full[0], 1); mbar_init(&slab_full[1], 1);
-      mbar_init(&slab_empty[0], 1); mbar_init(&slab_empty[1], 1);
-      mbar_init(acc_full, 1);
+      for (int i = 0; i < 4; ++i) { mbar_init(&slab_full[i], 1); mbar_init(&slab_empty[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps); }
       for (int s = 0; s < p.stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
       fence_mbar_init();
     }
@@ -96,97 +99,170 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // ------------------------------------------------ weight producer
+    // ------------------------------------------------ weight producer (1-D bulk copies)
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const size_t blk_off = static_cast<size_t>(nblk) * p.nc * p.ntaps * STAGE_BYTES;
-      for (int c = 0; c < p.nc; ++c) {
-        for (int t = 0; t < p.ntaps; ++t) {
+      for (int work = blockIdx.x; work < p.total_work; work += gridDim.x) {
+        const int nblk = work % p.n_blocks;
+        const size_t blk_off = static_cast<size_t>(nblk) * p.nc * p.ntaps * STAGE_BYTES;
+        for (int c = 0; c < p.nc; ++c) {
+          for (int t = 0; t < p.ntaps; ++t) {
 #pragma unroll
-          for (int wp = 0; wp < PLANES; ++wp) {
-            mbar_wait(&w_empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&w_full[stage], STAGE_BYTES);
-            const uint8_t* src = (wp ? p.w_lo : p.w_hi) + blk_off + static_cast<size_t>(c * p.ntaps + t) * STAGE_BYTES;
-            bulk_load_1d(wst + stage * STAGE_BYTES, src, STAGE_BYTES, &w_full[stage]);
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            for (int wp = 0; wp < PLANES; ++wp) {
+              mbar_wait(&w_empty[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&w_full[stage], STAGE_BYTES);
+              const uint8_t* src = (wp ? p.w_lo : p.w_hi) + blk_off + static_cast<size_t>(c * p.ntaps + t) * STAGE_BYTES;
+              bulk_load_1d(wst + stage * STAGE_BYTES, src, STAGE_BYTES, &w_full[stage]);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
           }
         }
+        if (p.w_resident) break;  // every tile is in shared memory now and stays there
       }
     }
   } else if (warp == 2) {
     // ------------------------------------------------ activation slab producer (TMA)
     if (lane == 0) {
-      for (int c = 0; c < p.nc; ++c) {
-        const int buf = c % p.nbuf;
-        const uint32_t use = static_cast<uint32_t>(c / p.nbuf);
-        mbar_wait(&slab_empty[buf], (use & 1) ^ 1);
-        mbar_arrive_expect_tx(&slab_full[buf], PLANES * slab_bytes);
+      int buf = 0; uint32_t phase = 0;
+      for (int work = blockIdx.x; work < p.total_work; work += gridDim.x) {
+        const int mt = work / p.n_blocks;
+        const int b = mt / p.tiles_per_item;
+        const int m0 = (mt - b * p.tiles_per_item) * (MS * 128);
+        for (int c = 0; c < p.nc; ++c) {
+          mbar_wait(&slab_empty[buf], phase ^ 1);
+          mbar_arrive_expect_tx(&slab_full[buf], PLANES * slab_bytes);
 #pragma unroll
-        for (int pl = 0; pl < PLANES; ++pl) {
-          uint8_t* dst = slab + (buf * PLANES + pl) * slab_bytes;
-          for (int bx = 0; bx < p.nboxes; ++bx)
-            tma_load_3d(dst + bx * p.box_rows * ROWB, pl ? &map_lo : &map_hi, &slab_full[buf], c * KC,
-                        m0 + p.min_off + bx * p.box_rows, b);
+          for (int pl = 0; pl < PLANES; ++pl) {
+            uint8_t* dst = slab + (buf * PLANES + pl) * slab_bytes;
+            for (int bx = 0; bx < p.nboxes; ++bx)
+              tma_load_3d(dst + bx * p.box_rows * ROWB, pl ? &map_lo : &map_hi, &slab_full[buf], c * KC,
+                          m0 + p.min_off + bx * p.box_rows, b);
+          }
+          if (++buf == p.nbuf) { buf = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, N_T);
-      int stage = 0; uint32_t phase = 0;
+    // ------------------------------------------------ MMA issuer
+    // The whole warp walks the loops (so every address / descriptor stays warp-uniform and lives in
+    // uniform registers); one elected lane issues the tcgen05.mma / tcgen05.commit instructions.
+    constexpr uint32_t idesc = umma_idesc_bf16(128, N_T);
+    // descriptor hi word: SBO>>4 at [0,14), version 1 at [14,16), layout at [29,32)
+    constexpr uint32_t desc_hi = ((SBO >> 4) & 0x3FFFu) | (1u << 14) | (SwzOf<KC>::layout << 29);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t slab_lo = (smem_u32(slab) & 0x3FFFFu) >> 4;
+    const uint32_t wst_lo = (smem_u32(wst) & 0x3FFFFu) >> 4;
+    const uint32_t slab_step = static_cast<uint32_t>(slab_bytes) >> 4;
+    int stage = 0; uint32_t wphase = 0;
+    int buf = 0; uint32_t sphase = 0;
+    int it = 0;
+    for (int work = blockIdx.x; work < p.total_work; work += gridDim.x, ++it) {
+      const int ab = it & 1;
+      mbar_wait(&acc_empty[ab], ((it >> 1) & 1) ^ 1);  // epilogue drained this accumulator buffer
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_u + ab * ACC_COLS;
       for (int c = 0; c < p.nc; ++c) {
-        const int buf = c % p.nbuf;
-        const uint32_t use = static_cast<uint32_t>(c / p.nbuf);
-        mbar_wait(&slab_full[buf], use & 1);
+        mbar_wait(&slab_full[buf], sphase);
         tc_fence_after();
         for (int t = 0; t < p.ntaps; ++t) {
+          const uint32_t tap_lo = (static_cast<uint32_t>(p.tap_row[t]) * ROWB) >> 4;
 #pragma unroll
           for (int wp = 0; wp < PLANES; ++wp) {
-            mbar_wait(&w_full[stage], phase);
-            tc_fence_after();
-            const uint32_t w_base = smem_u32(wst + stage * STAGE_BYTES);
+            if (!p.w_resident || it == 0) {
+              mbar_wait(&w_full[stage], wphase);
+              tc_fence_after();
+            }
+            const uint32_t b_lo = wst_lo + static_cast<uint32_t>(stage) * (STAGE_BYTES >> 4);
             const int n_a = (SPLIT && wp == 0) ? 2 : 1;  // W_hi meets A_hi and A_lo; W_lo meets A_hi
-            for (int ap = 0; ap < n_a; ++ap) {
-              const uint32_t a_plane = smem_u32(slab + (buf * PLANES + ap) * slab_bytes);
-              for (int ms = 0; ms < ms_count; ++ms) {
-                const uint32_t a_base = a_plane + static_cast<uint32_t>(ms * 128 + p.tap_row[t]) * ROWB;
+            if (elect_one()) {
+              // Straight-line issue: all MS sub-tiles are always issued (rows past the end of the item
+              // are TMA zero fill and their results are never stored), so every descriptor is the tap
+              // base plus a compile-time constant and the issue rate reaches the tensor-core floor.
 #pragma unroll
-                for (int ks = 0; ks < KSTEPS; ++ks) {
-                  const uint32_t a_addr = a_base + ks * 32;
-                  const uint64_t adesc =
-                      umma_smem_desc(a_addr, 0, SBO, SwzOf<KC>::layout, desc_base_offset(a_addr, p.desc_mode));
-                  const uint64_t bdesc = umma_smem_desc(w_base + ks * 32, 0, SBO, SwzOf<KC>::layout, 0);
-                  const uint32_t accumulate = (c | t | wp | ap | ks) != 0 ? 1u : 0u;
-                  umma_bf16(tmem_base + ms * N_T, adesc, bdesc, idesc, accumulate);
+              for (int ap = 0; ap < (SPLIT ? 2 : 1); ++ap) {
+                if (ap < n_a) {
+                  const uint32_t a_lo0 = slab_lo + static_cast<uint32_t>(buf * PLANES + ap) * slab_step + tap_lo;
+                  const uint32_t first = (c | t | wp | ap) != 0 ? 1u : 0u;
+#pragma unroll
+                  for (int ks = 0; ks < KSTEPS; ++ks) {
+#pragma unroll
+                    for (int ms = 0; ms < MS; ++ms)
+                      umma_bf16_lohi(tmem_acc + ms * N_T, a_lo0 + static_cast<uint32_t>(ms * ((128 * ROWB) >> 4) + ks * 2),
+                                     b_lo + ks * 2, desc_hi, idesc, ks == 0 ? first : 1u);
+                  }
                 }
               }
+              if (!p.w_resident) umma_commit(&w_empty[stage]);  // frees the stage once these MMAs retire
             }
-            umma_commit(&w_empty[stage]);  // frees the weight stage once these MMAs retire
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; wphase ^= 1; }
           }
         }
-        umma_commit(&slab_empty[buf]);
+        if (elect_one()) umma_commit(&slab_empty[buf]);
+        __syncwarp();
+        if (++buf == p.nbuf) { buf = 0; sphase ^= 1; }
       }
-      umma_commit(acc_full);
+      if (elect_one()) umma_commit(&acc_full[ab]);
+      __syncwarp();
     }
   } else {
-    // ------------------------------------------------ epilogue: TMEM -> registers -> HBM
+    // ------------------------------------------------ epilogue: TMEM -> regs -> smem transpose -> HBM
+    // Warp e (0..15) may only touch TMEM lanes [32*(warp%4), +32).  The four warps that share a lane
+    // quarter split the (sub-tile, 16-column chunk) items of the tile between them.  tcgen05.ld gives
+    // one row per thread; a swizzled 2 KB staging tile turns that into 4 lanes per row so every
+    // global access is a whole number of 32 B sectors (64 B fp32 / 32 B bf16 per row).
+    const int e = warp - 3;
     const int quarter = warp & 3;
-    const int row_in_tile = quarter * 32 + lane;
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    for (int ms = 0; ms < ms_count; ++ms) {
-      const long long q = static_cast<long long>(m0) + ms * 128 + row_in_tile;
-#pragma unroll 1
-      for (int c0 = 0; c0 < N_T; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + ms * N_T + c0, r);
+    const int sub = e >> 2;
+    float* stg = staging + e * kStageFloats;
+    const int c4 = lane & 3, rsub = lane >> 2;
+    int it = 0;
+    for (int work = blockIdx.x; work < p.total_work; work += gridDim.x, ++it) {
+      const int nblk = work % p.n_blocks;
+      const int mt = work / p.n_blocks;
+      const int b = mt / p.tiles_per_item;
+      const int m0 = (mt - b * p.tiles_per_item) * (MS * 128);
+      int ms_count = (p.rows - m0 + 127) / 128;
+      ms_count = ms_count > MS ? MS : ms_count;
+      const int ab = it & 1;
+      const uint32_t tmem_acc = tmem_base + ab * ACC_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
+      mbar_wait(&acc_full[ab], (it >> 1) & 1);
+      tc_fence_after();
+      const int items = ms_count * CHUNKS;
+      bool released = false;
+      for (int j = sub; j < items; j += 4) {
+        const int ms = j / CHUNKS, c0 = (j - ms * CHUNKS) * 16;
+        uint32_t r[16];
+        tmem_ld_32x16(tmem_acc + ms * N_T + c0, r);
         tmem_ld_wait();
+        if (j + 4 >= items) {  // last TMEM read of this warp for this item: hand the buffer back early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[ab]);
+          released = true;
+        }
+        // row `lane` -> staging, 16 B chunk k stored at position k ^ ((row >> 1) & 3): conflict-free
+        // for both the row-per-thread writes and the 4-lanes-per-row reads
 #pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          epilogue_vec4(p.epi, b, q, nblk * N_T + c0 + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]),
-                        __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+        for (int k4 = 0; k4 < 4; ++k4)
+          *reinterpret_cast<uint4*>(stg + lane * 16 + ((k4 ^ ((lane >> 1) & 3)) << 2)) =
+              make_uint4(r[4 * k4], r[4 * k4 + 1], r[4 * k4 + 2], r[4 * k4 + 3]);
+        __syncwarp();
+        float v[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = i * 8 + rsub;
+          const float4 t4 = *reinterpret_cast<const float4*>(stg + row * 16 + ((c4 ^ ((row >> 1) & 3)) << 2));
+          v[i][0] = t4.x; v[i][1] = t4.y; v[i][2] = t4.z; v[i][3] = t4.w;
+        }
+        __syncwarp();
+        epilogue_rows<4>(p.epi, b, static_cast<long long>(m0) + ms * 128 + quarter * 32 + rsub, 8,
+                         nblk * N_T + c0 + c4 * 4, v);
+      }
+      if (!released) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[ab]);
       }
     }
   }
@@ -202,12 +278,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
 size_t conv_tc_smem_bytes(int n_t, int kc, bool split, int slab_rows, int nbuf, int stages) {
   const int rowb = kc * 2, planes = split ? 2 : 1;
   size_t slab = (static_cast<size_t>(nbuf) * planes * slab_rows * rowb + 1023) & ~size_t(1023);
-  return 1024 + slab + static_cast<size_t>(stages) * n_t * rowb + (5 + 2 * stages) * 8 + 16;
+  return 1024 + slab + static_cast<size_t>(stages) * n_t * rowb + kEpiWarps * kStageFloats * 4 + (12 + 2 * stages) * 8 + 16;
 }
 
 template <int N_T, int KC, int MS, bool SPLIT>
 static cudaError_t launch_one(const CUtensorMap& mh, const CUtensorMap& ml, const TcConvParams& p, int n_blocks,
-                              size_t smem, cudaStream_t st) {
+                              size_t smem, int grid_ctas, cudaStream_t st) {
   auto kern = conv_tc_kernel<N_T, KC, MS, SPLIT>;
   static size_t configured = 0;  // per-instantiation high-water mark
   if (smem > configured) {
@@ -215,25 +291,25 @@ static cudaError_t launch_one(const CUtensorMap& mh, const CUtensorMap& ml, cons
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  dim3 grid(static_cast<unsigned>(p.B * p.tiles_per_item), static_cast<unsigned>(n_blocks));
-  kern<<<grid, kTcThreads, smem, st>>>(mh, ml, p);
+  (void)n_blocks;
+  kern<<<grid_ctas, kTcThreads, smem, st>>>(mh, ml, p);
   return cudaGetLastError();
 }
 
 template <int N_T, int KC, int MS>
 static cudaError_t launch_split(bool split, const CUtensorMap& mh, const CUtensorMap& ml, const TcConvParams& p,
-                                int n_blocks, size_t smem, cudaStream_t st) {
-  return split ? launch_one<N_T, KC, MS, true>(mh, ml, p, n_blocks, smem, st)
-               : launch_one<N_T, KC, MS, false>(mh, ml, p, n_blocks, smem, st);
+                                int n_blocks, size_t smem, int grid_ctas, cudaStream_t st) {
+  return split ? launch_one<N_T, KC, MS, true>(mh, ml, p, n_blocks, smem, grid_ctas, st)
+               : launch_one<N_T, KC, MS, false>(mh, ml, p, n_blocks, smem, grid_ctas, st);
 }
 
-// Valid (N_T, KC, MS): N_T in {32,64,128,256}, KC in {32,64}, MS*N_T <= 512, MS in {1,2,4}.
+// Valid (N_T, KC, MS): N_T in {32,64,128,256}, KC in {32,64}, MS in {1,2,4}, 2*MS*N_T <= 512.
 cudaError_t launch_conv_tc(int n_t, int kc, int ms, bool split, const CUtensorMap& mh, const CUtensorMap& ml,
-                           const TcConvParams& p, int n_blocks, size_t smem, cudaStream_t st) {
+                           const TcConvParams& p, int n_blocks, size_t smem, int grid_ctas, cudaStream_t st) {
 #define HG_CASE(NT, KCV, MSV) \
-  if (n_t == NT && kc == KCV && ms == MSV) return launch_split<NT, KCV, MSV>(split, mh, ml, p, n_blocks, smem, st);
-  HG_CASE(256, 64, 1) HG_CASE(256, 64, 2)
-  HG_CASE(128, 64, 1) HG_CASE(128, 64, 2) HG_CASE(128, 64, 4)
+  if (n_t == NT && kc == KCV && ms == MSV) return launch_split<NT, KCV, MSV>(split, mh, ml, p, n_blocks, smem, grid_ctas, st);
+  HG_CASE(256, 64, 1)
+  HG_CASE(128, 64, 1) HG_CASE(128, 64, 2)
   HG_CASE(64, 64, 1) HG_CASE(64, 64, 2) HG_CASE(64, 64, 4)
   HG_CASE(64, 32, 1) HG_CASE(64, 32, 2) HG_CASE(64, 32, 4)
   HG_CASE(32, 64, 1) HG_CASE(32, 64, 2) HG_CASE(32, 64, 4)

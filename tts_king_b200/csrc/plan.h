@@ -41,6 +41,7 @@ struct Layer {
 
 struct TcTiling {
   int ms = 1, stages = 2, nbuf = 1, slab_rows = 0, box_rows = 0, nboxes = 1, min_off = 0;
+  bool resident = false;  // all weight tiles stay in shared memory
   size_t smem = 0;
 };
 
@@ -57,6 +58,7 @@ struct HgPlan {
   std::map<std::string, int> by_name;
   int desc_mode = 0;  // measured on B200 (selftest.cu): UMMA swizzle phase comes from absolute smem address bits
   int force_ms = 0, force_stages = 0;
+  int ctas_per_sm = 1;  // persistent grid = min(work, SMs * ctas_per_sm)
   bool force_ffma = false;  // HG_FORCE_FFMA=1: route every layer to the CUDA-core kernel
   std::mutex mu;
   std::map<hg::MapKey, CUtensorMap> maps;

@@ -83,6 +83,87 @@ __global__ void __launch_bounds__(128) selftest_kernel(const __nv_bfloat16* __re
   if (warp == 0) tmem_dealloc(tmem, 64);
 }
 
+// ------------------------------------------------------------------------------------------------
+// UMMA issue/throughput microbenchmark: one CTA, one elected lane issues `n_mma` back-to-back
+// tcgen05.mma (M=128, N, K=16, bf16, SS operands from a 128B-swizzled slab) and the warp times the
+// span from first issue to commit-arrival with clock64.  n_acc = how many TMEM accumulators the
+// chain rotates over (1 = fully dependent accumulation).
+template <int N>
+__global__ void __launch_bounds__(128) umma_bench_kernel(int n_mma, int n_acc, int shift_rows, long long* out_cycles) {
+  extern __shared__ uint8_t bsm_raw[];
+  uint8_t* bsm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bsm_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = bsm;                   // 192 rows x 128 B
+  uint8_t* sb = bsm + 192 * 128;       // N rows x 128 B
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_ptr;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int e = threadIdx.x; e < (192 + N) * 32; e += 128) reinterpret_cast<uint32_t*>(bsm)[e] = 0x3c003c00u + e;
+  fence_proxy_async();
+  if (warp == 0) {
+    if (lane == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    __syncwarp();
+    tmem_alloc(&tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_ptr;
+  if (warp == 0) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, N);
+    constexpr uint32_t desc_hi = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (UMMA_LAYOUT_SW128 << 29);
+    const uint32_t a_lo = (smem_u32(sa) & 0x3FFFFu) >> 4, b_lo = (smem_u32(sb) & 0x3FFFFu) >> 4;
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    long long t0 = clock64();
+    if (elect_one()) {
+      // tight issue loop: 8 MMAs per iteration, descriptors are loop-invariant adds of constants
+      const uint32_t acc1 = tm + (n_acc > 1 ? N : 0), sh = static_cast<uint32_t>(shift_rows) * 8;
+      for (int i = 0; i < n_mma; i += 8) {
+        umma_bf16_lohi(tm, a_lo, b_lo, desc_hi, idesc, 1u);
+        umma_bf16_lohi(acc1, a_lo + 2, b_lo + 2, desc_hi, idesc, 1u);
+        umma_bf16_lohi(tm, a_lo + 4, b_lo + 4, desc_hi, idesc, 1u);
+        umma_bf16_lohi(acc1, a_lo + 6, b_lo + 6, desc_hi, idesc, 1u);
+        umma_bf16_lohi(tm, a_lo + sh, b_lo, desc_hi, idesc, 1u);
+        umma_bf16_lohi(acc1, a_lo + sh + 2, b_lo + 2, desc_hi, idesc, 1u);
+        umma_bf16_lohi(tm, a_lo + sh + 4, b_lo + 4, desc_hi, idesc, 1u);
+        umma_bf16_lohi(acc1, a_lo + sh + 6, b_lo + 6, desc_hi, idesc, 1u);
+      }
+      umma_commit(&bar);
+    }
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    if (lane == 0) *out_cycles = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <int N>
+static void bench_one(std::string& rep, long long* d_out) {
+  const int smem = 1024 + (192 + N) * 128;
+  cudaFuncSetAttribute(umma_bench_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int n_acc : {1, 2}) {
+    if (n_acc * N > 512) continue;
+    for (int shift : {0, 1}) {
+      long long c1 = 0, c2 = 0;
+      for (int rep_i = 0; rep_i < 2; ++rep_i) {
+        umma_bench_kernel<N><<<1, 128, smem>>>(256, n_acc, shift, d_out);
+        cudaDeviceSynchronize();
+        cudaMemcpy(&c1, d_out, 8, cudaMemcpyDeviceToHost);
+        umma_bench_kernel<N><<<1, 128, smem>>>(1280, n_acc, shift, d_out);
+        cudaDeviceSynchronize();
+        cudaMemcpy(&c2, d_out, 8, cudaMemcpyDeviceToHost);
+      }
+      char b[160];
+      snprintf(b, sizeof(b), "umma_bench M=128 N=%3d K=16 n_acc=%d row_shift=%d: %.1f cycles/MMA (256: %lld, 1280: %lld)\n", N,
+               n_acc, shift, (c2 - c1) / 1024.0, c1, c2);
+      rep += b;
+    }
+  }
+}
+
 static void appendf(std::string& s, const char* fmt, ...) {
   char b[256];
   va_list ap;
@@ -140,6 +221,13 @@ int run_tcgen05_selftest(char* buf, size_t len) {
   std::string rep;
   int f = run_kc<64>(rep);
   if (f < 1000) f += run_kc<32>(rep);
+  if (f < 1000) {
+    long long* d_out = nullptr;
+    if (cudaMalloc(&d_out, 8) == cudaSuccess) {
+      bench_one<32>(rep, d_out); bench_one<64>(rep, d_out); bench_one<128>(rep, d_out); bench_one<256>(rep, d_out);
+      cudaFree(d_out);
+    }
+  }
   if (buf && len) {
     strncpy(buf, rep.c_str(), len - 1);
     buf[len - 1] = 0;

@@ -288,7 +288,8 @@ class Generator(nn.Module):
             t = table[li]
             rows.append(dict(name=t.name.decode(), kind=t.kind, c_in=t.c_in, c_out=t.c_out, k=t.k, dilation=t.dilation,
                              stride=t.stride, tensor_core=bool(t.tensor_core), n_tile=t.n_tile, k_chunk=t.k_chunk,
-                             m_subtiles=t.m_subtiles, stages=t.stages, smem_bytes=t.smem_bytes, ms=ms))
+                             m_subtiles=t.m_subtiles, stages=t.stages, smem_bytes=t.smem_bytes,
+                             weights_resident=bool(t.weights_resident), slab_buffers=t.slab_buffers, ms=ms))
         return rows
 
     # ------------------------------------------------------------------ internals
