@@ -146,6 +146,15 @@ HG_API int hg_op_conv_transpose1d(int device, int precision, const float* x, int
                            float in_slope, float* y, void* stream);
 HG_API int hg_op_conv_post(int device, const float* x, int B, int L, int C, const float* weight,
                     const float* bias, float* y, void* stream);
+/*
+ * One ResBlock1 pair, hifi/models.py:90-94, through the fused kernel (bf16 operands):
+ *   y = c2(leaky_relu(c1(leaky_relu(x, in_slope)), in_slope)) + residual
+ * c1: Conv1d(C,C,k,dilation=d1), c2: Conv1d(C,C,k,dilation=1); C in {32, 64}.  Fails with HG_EINVAL
+ * when the shape is not covered by the fused kernel.
+ */
+HG_API int hg_op_conv_pair(int device, const float* x, int B, int L, int C, int k, int d1,
+                           const float* w1, const float* b1, const float* w2, const float* b2,
+                           float in_slope, const float* residual, float* y, void* stream);
 
 /*
  * Per-layer timing (bench.py's roofline pass; the reference has no profiler).

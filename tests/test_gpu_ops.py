@@ -164,6 +164,39 @@ def test_resblock1_block_level(prec):
     assert err <= (2e-5 if prec == "fp32" else 5e-2) * r.abs().max().item(), err
 
 
+@pytest.mark.parametrize("C,k,d1", [(64, 3, 1), (64, 7, 3), (64, 11, 5), (32, 3, 5), (32, 7, 1), (32, 11, 5)])
+@pytest.mark.parametrize("n", [1, 100, 246, 247, 502, 503, 1500])
+def test_fused_pair_parity(C, k, d1, n):
+    """The fused ResBlock-pair kernel (conv_pair_tc.cu) against the fp64 restatement of
+    hifi/models.py:90-94 with the kernel's operand model (bf16 operands, bf16 intermediate);
+    lengths straddle the 246/502-row output tiles."""
+    L = _native.lib()
+    g = torch.Generator().manual_seed(C * 1000 + k * 10 + d1 + n)
+    B = 2
+    x = torch.randn(B, C, n, generator=g)
+    w1 = torch.randn(C, C, k, generator=g) / (C * k) ** 0.5
+    b1 = torch.randn(C, generator=g) * 0.1
+    w2 = torch.randn(C, C, k, generator=g) / (C * k) ** 0.5
+    b2 = torch.randn(C, generator=g) * 0.1
+    res = torch.randn(B, C, n, generator=g)
+    dev = torch.device("cuda", 0)
+    xc = x.transpose(1, 2).contiguous().to(dev)
+    rc_ = res.transpose(1, 2).contiguous().to(dev)
+    y = torch.full((B, n, C), float("nan"), device=dev)
+    _native.check(L.hg_op_conv_pair(0, xc.data_ptr(), B, n, C, k, d1, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                                    b2.data_ptr(), 0.1, rc_.data_ptr(), y.data_ptr(),
+                                    torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    y = y.cpu().transpose(1, 2)
+    a = bf16_round(F.leaky_relu(x, 0.1))
+    xt = F.conv1d(a, bf16_round(w1), b1.double(), dilation=d1, padding=(k * d1 - d1) // 2)
+    xt = bf16_round(F.leaky_relu(xt.float(), 0.1))  # the kernel rounds fp32 accum + bias, then lrelu, to bf16
+    ref = F.conv1d(xt, bf16_round(w2), b2.double(), padding=(k - 1) // 2) + res.double()
+    assert not torch.isnan(y).any()
+    # the intermediate's bf16 rounding can flip on fp32-vs-fp64 accumulation noise: allow a few bf16 ulps of xt
+    assert (y.double() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+
+
 def test_tcgen05_descriptor_selftest():
     n, report = _native.selftest(0)
     import os

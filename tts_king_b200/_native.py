@@ -71,13 +71,15 @@ def lib() -> ctypes.CDLL:
     L.hg_op_conv_transpose1d.argtypes = [i, i, vp, i, i, i, vp, vp, i, i, i, f, vp, vp]
     L.hg_op_conv_post.argtypes = [i, vp, i, i, i, vp, vp, vp, vp]
     L.hg_selftest_tcgen05.argtypes = [i, ctypes.c_char_p, sz]
+    L.hg_op_conv_pair.argtypes = [i, vp, i, i, i, i, i, vp, vp, vp, vp, f, vp, vp, vp]
     L.hg_layer_count.argtypes = [vp, ctypes.POINTER(i)]
     L.hg_layer_info.argtypes = [vp, i, i, ctypes.POINTER(HgLayerInfo)]
     L.hg_profile_forward.argtypes = [vp, vp, i64, i64, i64, i, i, vp, i, f, i, vp, sz, vp, ctypes.POINTER(i),
                                      ctypes.POINTER(f), i, ctypes.POINTER(i)]
     for name in ("hg_plan_create", "hg_plan_upload_weight", "hg_plan_finalize", "hg_workspace_bytes",
                  "hg_forward_launches", "hg_forward", "hg_plan_destroy", "hg_op_conv1d",
-                 "hg_op_conv_transpose1d", "hg_op_conv_post", "hg_selftest_tcgen05", "hg_layer_count", "hg_layer_info",
+                 "hg_op_conv_transpose1d", "hg_op_conv_post", "hg_op_conv_pair", "hg_selftest_tcgen05", "hg_layer_count",
+                 "hg_layer_info",
                  "hg_profile_forward"):
         getattr(L, name).restype = i
     if L.hg_abi_version() != 1:

@@ -26,6 +26,9 @@ cudaError_t launch_mel_to_operand(const float* mel, long long sB, long long sC, 
 cudaError_t launch_f32_to_operand(const float* x, long long n, float slope, int a_fmt, void* a0, void* a1,
                                   cudaStream_t st);
 int run_tcgen05_selftest(char* buf, size_t len);
+size_t conv_pair_smem_bytes(int c, int slab_rows, int t_rows, int t_bufs, int stages);
+cudaError_t launch_conv_pair_tc(int c, const CUtensorMap& m, const CUtensorMap& mr, const TcPairParams& p, size_t smem,
+                                int grid, cudaStream_t st);
 }  // namespace hg
 
 using namespace hg;
@@ -126,6 +129,34 @@ static int make_operand_map(HgPlan* plan, const void* ptr, int L, int B, int cpi
   return HG_OK;
 }
 
+// fp32 tensor [B][L][C] -> 3-D map with a {32 channels, 32 rows, 1} box, 128B swizzle: the residual
+// tiles the fused-pair epilogue pulls straight into its staging slots.
+static int make_f32_tile_map(HgPlan* plan, const void* ptr, int L, int B, int c, CUtensorMap* out) {
+  MapKey key(ptr, L, B, c, -32, 32);
+  {
+    std::lock_guard<std::mutex> g(plan->mu);
+    auto it = plan->maps.find(key);
+    if (it != plan->maps.end()) { *out = it->second; return HG_OK; }
+  }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(HG_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(c) * 4, static_cast<cuuint64_t>(L) * c * 4};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(HG_ECUDA, "cuTensorMapEncodeTiled (fp32 tile) failed (%d)", static_cast<int>(r));
+  {
+    std::lock_guard<std::mutex> g(plan->mu);
+    plan->maps[key] = m;
+  }
+  *out = m;
+  return HG_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // layer table
 static int env_int(const char* name, int dflt) {
@@ -198,6 +229,7 @@ extern "C" int hg_plan_create(const HgConfig* cfg, int device, HgPlan** out) {
   p->force_stages = env_int("HG_TC_STAGES", 0);
   p->force_ffma = env_int("HG_FORCE_FFMA", 0) != 0;
   p->ctas_per_sm = env_int("HG_TC_CTAS_PER_SM", 1);
+  p->fuse_pairs = env_int("HG_FUSE_PAIRS", 1) != 0;
   const int uic = cfg->upsample_initial_channel;
   p->layers.push_back(make_conv("conv_pre", cfg->num_mels, uic, 7, 1));
   for (int i = 0; i < cfg->num_upsamples; ++i) {
@@ -492,6 +524,91 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
 }
 
 // ------------------------------------------------------------------------------------------------
+// fused ResBlock1 pair (conv_pair_tc.cu): bf16 mode, C in {32, 64}
+struct PairTiling {
+  int ms = 0, slab_rows = 0, box_rows = 0, nboxes = 0, t_rows = 0, t_bufs = 1, stages = 0, r_out = 0;
+  bool resident = false;
+  size_t smem = 0;
+};
+
+static bool pair_fusable(const HgPlan* plan, const Layer& l1, const Layer& l2, int precision, PairTiling* t) {
+  if (!plan->fuse_pairs || precision != HG_PREC_BF16 || plan->force_ffma) return false;
+  if (l1.kind != L_CONV || l2.kind != L_CONV || !l1.tc || !l2.tc) return false;
+  const int c = l1.cin;
+  if ((c != 32 && c != 64) || l1.cout != c || l2.cin != c || l2.cout != c) return false;
+  if (l1.k != l2.k || l2.dil != 1 || (l1.k & 1) == 0 || l1.k > kMaxTaps) return false;
+  const int rowb = c * 2;
+  t->ms = 128 / c;  // MS * N_T = 128 accumulator columns per buffer
+  const int mt = t->ms * 128;
+  t->r_out = mt - (l1.k - 1);
+  if (t->r_out < 64) return false;
+  const int need = mt + l1.dil * (l1.k - 1);
+  t->nboxes = (need + 255) / 256;
+  const int align_rows = 1024 / rowb * 2;  // keeps every buffer a multiple of 1024 bytes
+  t->box_rows = (((need + t->nboxes - 1) / t->nboxes) + align_rows - 1) / align_rows * align_rows;
+  if (t->box_rows > 256) return false;
+  t->slab_rows = t->nboxes * t->box_rows;
+  t->t_rows = (mt + l1.k - 1 + 15) / 16 * 16;
+  const size_t kMaxSmem = 227 * 1024;
+  const int all = 2 * l1.k;
+  // preference order: resident weights + double-buffered xt, resident + single xt, streamed ring
+  t->stages = 0;
+  for (int tb : {2, 1}) {
+    if (conv_pair_smem_bytes(c, t->slab_rows, t->t_rows, tb, all) <= kMaxSmem) {
+      t->resident = true; t->stages = all; t->t_bufs = tb;
+      break;
+    }
+  }
+  if (!t->stages) {
+    t->resident = false;
+    t->t_bufs = 1;
+    int s = 8;
+    while (s >= 2 && conv_pair_smem_bytes(c, t->slab_rows, t->t_rows, 1, s) > kMaxSmem) --s;
+    if (s < 2) return false;
+    t->stages = s;
+    if (conv_pair_smem_bytes(c, t->slab_rows, t->t_rows, 2, std::min(s, 4)) <= kMaxSmem && s >= 4) {
+      t->t_bufs = 2;
+      while (conv_pair_smem_bytes(c, t->slab_rows, t->t_rows, 2, t->stages) > kMaxSmem) --t->stages;
+    }
+  }
+  t->smem = conv_pair_smem_bytes(c, t->slab_rows, t->t_rows, t->t_bufs, t->stages);
+  return true;
+}
+
+static int run_pair(HgPlan* plan, const Layer& l1, const Layer& l2, const PairTiling& t, int B, int L,
+                    const OperandBuf& in, EpiParams epi, float slope, cudaStream_t st) {
+  const int c = l1.cin;
+  epi.bias = l2.bias;
+  epi.a_fmt = A_BF16;
+  epi.out_batch_stride = static_cast<long long>(L) * c;
+  epi.out_extent = static_cast<long long>(L) * c;
+  epi.out_row_stride = c;
+  epi.out_offset = 0;
+  TcPairParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.L = L; p.r_out = t.r_out;
+  p.tiles_per_item = (L + t.r_out - 1) / t.r_out;
+  p.total_work = B * p.tiles_per_item;
+  p.k = l1.k; p.d1 = l1.dil;
+  p.slab_rows = t.slab_rows; p.box_rows = t.box_rows; p.nboxes = t.nboxes; p.t_rows = t.t_rows; p.t_bufs = t.t_bufs;
+  p.stages = t.stages; p.w_resident = t.resident ? 1 : 0;
+  p.w1 = l1.w_hi; p.w2 = l2.w_hi; p.bias1 = l1.bias; p.slope = slope;
+  p.epi = epi;
+  if (!epi.res) return fail(HG_ESTATE, "internal: fused pair without a residual");
+  CUtensorMap m, mr;
+  int rc = make_operand_map(plan, in.a0, L, B, c, c, t.box_rows, &m);
+  if (rc) return rc;
+  if ((rc = make_f32_tile_map(plan, epi.res, L, B, c, &mr))) return rc;
+  epi.res = nullptr;  // the kernel adds the residual from its TMA-loaded tile
+  p.epi = epi;
+  const int grid = std::min(p.total_work, plan->sm_count);
+  cudaError_t e = launch_conv_pair_tc(c, m, mr, p, t.smem, grid, st);
+  if (e != cudaSuccess) return fail(HG_ECUDA, "conv_pair_tc launch (%s): %s", l2.name.c_str(), cudaGetErrorString(e));
+  if (g_prof) prof_mark(static_cast<int>(&l2 - plan->layers.data()));
+  return HG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // workspace
 struct Workspace {
   float* F[3];
@@ -564,7 +681,17 @@ extern "C" int hg_forward_launches(const HgPlan* plan, int B, int T, int precisi
   int rc = check_fwd_args(plan, B, T, precision);
   if (rc) return rc;
   if (!launches) return fail(HG_EINVAL, "null launches");
-  *launches = static_cast<int>(plan->layers.size()) + 1;  // every layer + the mel repack
+  int n = static_cast<int>(plan->layers.size()) + 1;  // every layer + the mel repack
+  if (plan->cfg.resblock_type == 1) {
+    const int D = 3, U = plan->cfg.num_upsamples, K = plan->cfg.num_kernels;
+    int li = 1 + U;
+    for (int i = 0; i < U * K; ++i, li += 2 * D)
+      for (int m = 0; m < D; ++m) {
+        PairTiling pt;
+        if (pair_fusable(plan, plan->layers[li + m], plan->layers[li + D + m], precision, &pt)) --n;
+      }
+  }
+  *launches = n;
   return HG_OK;
 }
 
@@ -623,7 +750,10 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
       for (int m = 0; m < D; ++m) {
         const bool last_pair = m == D - 1;
         int a_conv_in = a_in;
-        if (c.resblock_type == 1) {
+        const Layer& l2 = plan->layers[c.resblock_type == 1 ? li + D + m : li + m];
+        PairTiling pt;
+        const bool fused = c.resblock_type == 1 && pair_fusable(plan, plan->layers[li + m], l2, precision, &pt);
+        if (c.resblock_type == 1 && !fused) {
           // xt = c1(leaky_relu(x)); only leaky_relu(xt) is consumed  :90-92
           const int a_t = 2;
           EpiParams ep; memset(&ep, 0, sizeof(ep));
@@ -631,7 +761,6 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
           if ((rc = run_layer(plan, plan->layers[li + m], precision, B, L, ws.A[a_in], ep, st))) return rc;
           a_conv_in = a_t;
         }
-        const Layer& l2 = plan->layers[c.resblock_type == 1 ? li + D + m : li + m];
         // x = c2(xt) + x  :93-94 (ResBlock2: x = c(leaky_relu(x)) + x  :136-138)
         EpiParams ep; memset(&ep, 0, sizeof(ep));
         ep.res = res; ep.slope = slope;
@@ -657,7 +786,12 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
             }
           }
         }
-        if ((rc = run_layer(plan, l2, precision, B, L, ws.A[a_conv_in], ep, st))) return rc;
+        if (fused) {
+          // c1 and c2 in one kernel; xt never leaves shared memory  (conv_pair_tc.cu)
+          if ((rc = run_pair(plan, plan->layers[li + m], l2, pt, B, L, ws.A[a_conv_in], ep, slope, st))) return rc;
+        } else if ((rc = run_layer(plan, l2, precision, B, L, ws.A[a_conv_in], ep, st))) {
+          return rc;
+        }
       }
       li += c.resblock_type == 1 ? 2 * D : D;
     }
@@ -806,6 +940,48 @@ extern "C" int hg_op_conv_post(int device, const float* x, int B, int L, int C, 
   free_layer(l);
   if (e != cudaSuccess) return fail(HG_ECUDA, "conv_post: %s", cudaGetErrorString(e));
   if (es != cudaSuccess) return fail(HG_ECUDA, "conv_post execution: %s", cudaGetErrorString(es));
+  return HG_OK;
+}
+
+extern "C" int hg_op_conv_pair(int device, const float* x, int B, int L, int C, int k, int d1, const float* w1,
+                               const float* b1, const float* w2, const float* b2, float in_slope, const float* residual,
+                               float* y, void* stream) {
+  if (!x || !w1 || !b1 || !w2 || !b2 || !y) return fail(HG_EINVAL, "null argument");
+  if (B < 1 || L < 1 || k < 1 || k > kMaxTaps || d1 < 1) return fail(HG_EINVAL, "bad shape");
+  int rc = check_device(device);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(device));
+  HgPlan plan;
+  plan.device = device;
+  plan.desc_mode = env_int("HG_DESC_MODE", 0);
+  {
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, device) == cudaSuccess) plan.sm_count = pr.multiProcessorCount;
+  }
+  plan.layers.push_back(make_conv("op.pair.c1", C, C, k, d1));
+  plan.layers.push_back(make_conv("op.pair.c2", C, C, k, 1));
+  Layer& l1 = plan.layers[0];
+  Layer& l2 = plan.layers[1];
+  PairTiling pt;
+  if (!pair_fusable(&plan, l1, l2, HG_PREC_BF16, &pt)) return fail(HG_EINVAL, "shape not covered by the fused pair kernel");
+  if ((rc = pack_layer(l1, w1, b1)) || (rc = pack_layer(l2, w2, b2))) { free_layer(l1); free_layer(l2); return rc; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long n = static_cast<long long>(B) * L * C;
+  void* a = nullptr;
+  cudaError_t e = cudaMalloc(&a, static_cast<size_t>(n) * 2);
+  if (e != cudaSuccess) { free_layer(l1); free_layer(l2); return fail(HG_ECUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
+  OperandBuf in;
+  in.a0 = a;
+  e = launch_f32_to_operand(x, n, in_slope, A_BF16, in.a0, nullptr, st);
+  EpiParams ep; memset(&ep, 0, sizeof(ep));
+  ep.res = residual; ep.out_x = y; ep.slope = 1.f;
+  rc = e == cudaSuccess ? run_pair(&plan, l1, l2, pt, B, L, in, ep, in_slope, st)
+                        : fail(HG_ECUDA, "f32_to_operand: %s", cudaGetErrorString(e));
+  cudaError_t es = cudaStreamSynchronize(st);
+  cudaFree(a);
+  free_layer(l1); free_layer(l2);
+  if (rc) return rc;
+  if (es != cudaSuccess) return fail(HG_ECUDA, "op execution failed: %s", cudaGetErrorString(es));
   return HG_OK;
 }
 

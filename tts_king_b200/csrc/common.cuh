@@ -104,7 +104,7 @@ __device__ __forceinline__ float lrelu_fast(float v, float slope) { return fmaxf
 
 template <int NR>
 __device__ __forceinline__ void epilogue_rows(const EpiParams& e, int b, long long q0, int row_step, int n,
-                                              float (&v)[NR][4]) {
+                                              float (&v)[NR][4], long long q_limit = 0x7fffffffffffffffLL) {
   const long long f0 = q0 * e.out_row_stride + n + e.out_offset;
   const long long fstep = static_cast<long long>(row_step) * e.out_row_stride;
   const long long base = static_cast<long long>(b) * e.out_batch_stride;
@@ -112,7 +112,7 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& e, int b, long lo
 #pragma unroll
   for (int i = 0; i < NR; ++i) {
     const long long f = f0 + i * fstep;
-    ok[i] = f >= 0 && f + 4 <= e.out_extent;
+    ok[i] = f >= 0 && f + 4 <= e.out_extent && q0 + static_cast<long long>(i) * row_step < q_limit;
   }
   const float4 bb = *reinterpret_cast<const float4*>(e.bias + n);
   if (e.res) {
@@ -187,6 +187,102 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& e, int b, long lo
   }
 }
 
+// Split form of epilogue_rows for software-pipelined epilogues: epi_prefetch issues the residual
+// loads of NR rows (and computes their validity) early; epi_finish consumes them later.
+template <int NR>
+__device__ __forceinline__ void epi_prefetch(const EpiParams& e, int b, long long q0, int row_step, int n,
+                                             long long q_limit, float4 (&r)[NR], unsigned& okmask) {
+  const long long f0 = q0 * e.out_row_stride + n + e.out_offset;
+  const long long fstep = static_cast<long long>(row_step) * e.out_row_stride;
+  const long long base = static_cast<long long>(b) * e.out_batch_stride;
+  okmask = 0;
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    const long long f = f0 + i * fstep;
+    if (f >= 0 && f + 4 <= e.out_extent && q0 + static_cast<long long>(i) * row_step < q_limit) okmask |= 1u << i;
+  }
+  if (e.res) {
+    const float* rp = e.res + base + f0;
+#pragma unroll
+    for (int i = 0; i < NR; ++i)
+      r[i] = (okmask >> i) & 1u ? *reinterpret_cast<const float4*>(rp + i * fstep) : make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+#pragma unroll
+    for (int i = 0; i < NR; ++i) r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+template <int NR>
+__device__ __forceinline__ void epi_finish(const EpiParams& e, int b, long long q0, int row_step, int n,
+                                           float (&v)[NR][4], const float4 (&r)[NR], unsigned okmask) {
+  const long long f0 = q0 * e.out_row_stride + n + e.out_offset;
+  const long long fstep = static_cast<long long>(row_step) * e.out_row_stride;
+  const long long base = static_cast<long long>(b) * e.out_batch_stride;
+  const float4 bb = *reinterpret_cast<const float4*>(e.bias + n);
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    v[i][0] = (v[i][0] + bb.x) + r[i].x; v[i][1] = (v[i][1] + bb.y) + r[i].y;
+    v[i][2] = (v[i][2] + bb.z) + r[i].z; v[i][3] = (v[i][3] + bb.w) + r[i].w;
+  }
+  if (e.acc_in) {
+    const float* ap = e.acc_in + base + f0;
+    float4 a[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i)
+      a[i] = (okmask >> i) & 1u ? *reinterpret_cast<const float4*>(ap + i * fstep) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      v[i][0] = a[i].x + v[i][0]; v[i][1] = a[i].y + v[i][1]; v[i][2] = a[i].z + v[i][2]; v[i][3] = a[i].w + v[i][3];
+    }
+  }
+  if (e.post_div > 0.f) {
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      v[i][0] = __fdiv_rn(v[i][0], e.post_div); v[i][1] = __fdiv_rn(v[i][1], e.post_div);
+      v[i][2] = __fdiv_rn(v[i][2], e.post_div); v[i][3] = __fdiv_rn(v[i][3], e.post_div);
+    }
+  }
+  if (e.out_x) {
+    float* xp = e.out_x + base + f0;
+#pragma unroll
+    for (int i = 0; i < NR; ++i)
+      if ((okmask >> i) & 1u) *reinterpret_cast<float4*>(xp + i * fstep) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+  }
+  if (e.out_a0) {
+    const float sl = e.slope;
+    if (e.a_fmt == A_BF16) {
+      __nv_bfloat16* hp = static_cast<__nv_bfloat16*>(e.out_a0) + base + f0;
+#pragma unroll
+      for (int i = 0; i < NR; ++i)
+        if ((okmask >> i) & 1u)
+          *reinterpret_cast<uint2*>(hp + i * fstep) = pack_bf16x4(lrelu_fast(v[i][0], sl), lrelu_fast(v[i][1], sl),
+                                                                  lrelu_fast(v[i][2], sl), lrelu_fast(v[i][3], sl));
+    } else if (e.a_fmt == A_BF16_SPLIT) {
+      __nv_bfloat16* hp = static_cast<__nv_bfloat16*>(e.out_a0) + base + f0;
+      __nv_bfloat16* lp = static_cast<__nv_bfloat16*>(e.out_a1) + base + f0;
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        if (!((okmask >> i) & 1u)) continue;
+        const float a0 = lrelu_fast(v[i][0], sl), a1 = lrelu_fast(v[i][1], sl), a2 = lrelu_fast(v[i][2], sl), a3 = lrelu_fast(v[i][3], sl);
+        const __nv_bfloat162 h01 = __floats2bfloat162_rn(a0, a1), h23 = __floats2bfloat162_rn(a2, a3);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+        pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+        *reinterpret_cast<uint2*>(hp + i * fstep) = pk;
+        *reinterpret_cast<uint2*>(lp + i * fstep) =
+            pack_bf16x4(a0 - __low2float(h01), a1 - __high2float(h01), a2 - __low2float(h23), a3 - __high2float(h23));
+      }
+    } else {
+      float* fp = static_cast<float*>(e.out_a0) + base + f0;
+#pragma unroll
+      for (int i = 0; i < NR; ++i)
+        if ((okmask >> i) & 1u)
+          *reinterpret_cast<float4*>(fp + i * fstep) = make_float4(lrelu_fast(v[i][0], sl), lrelu_fast(v[i][1], sl),
+                                                                   lrelu_fast(v[i][2], sl), lrelu_fast(v[i][3], sl));
+    }
+  }
+}
+
 // Scalar variant for layers whose width is not a multiple of 4 (tiny / narrow configs on the
 // CUDA-core path).
 __device__ __forceinline__ void epilogue_scalar(const EpiParams& e, int b, long long q, int n, float v) {
@@ -239,6 +335,29 @@ struct TcConvParams {
   const uint8_t* w_hi;  // packed swizzled weight tiles [n_blk][chunk][tap][N_T rows][KC]
   const uint8_t* w_lo;
   EpiParams epi;
+};
+
+// ------------------------------------------------------------------ fused ResBlock pair (tcgen05)
+// xt = lrelu(c1(a) + b1) stays in shared memory as the bf16 operand of c2; y = c2(xt) + b2 (+res ...)
+// goes through the usual epilogue (hifi/models.py:90-94).  C_in = C_out = C in {32, 64}.
+struct TcPairParams {
+  int B;
+  int L;               // sequence length (rows per item)
+  int r_out;           // output rows per tile = MS*128 - (k-1)
+  int tiles_per_item;  // ceil(L / r_out)
+  int total_work;      // B * tiles_per_item
+  int k;               // taps of both convs
+  int d1;              // dilation of c1 (c2 has dilation 1)
+  int slab_rows, box_rows, nboxes;  // input slab = MS*128 + d1*(k-1) rows (rounded)
+  int t_rows;          // rows of the intermediate tile buffer (MS*128 + k - 1, rounded to 16)
+  int t_bufs;          // 1 or 2 intermediate buffers
+  int stages;          // weight ring depth (== 2*k when w_resident)
+  int w_resident;
+  const uint8_t* w1;   // packed swizzled tiles [tap][C rows][C]  (conv 1)
+  const uint8_t* w2;   //                                         (conv 2)
+  const float* bias1;  // [C]
+  float slope;         // leaky_relu slope applied to xt (0.1)
+  EpiParams epi;       // epilogue of c2
 };
 
 // ------------------------------------------------------------------ CUDA-core (FFMA) conv

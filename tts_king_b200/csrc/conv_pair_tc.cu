@@ -1,0 +1,362 @@
+// conv_pair_tc.cu — one ResBlock1 pair as a single tcgen05 kernel (bf16 mode, C = 32 or 64):
+//
+//     xt = leaky_relu(c1(a) + b1)          dilated Conv1d, hifi/models.py:90-92
+//     y  = c2(xt) + b2 + x                 Conv1d d=1 + residual, hifi/models.py:93-94
+//     (+ MRF accumulate / divide / next operand copy, fused as in conv_tc.cu)
+//
+// Why: at 64/32 channels both convs are HBM-bound on their own; run separately
+// the pair moves 16 B per element (a, xt written, xt read, x read, x written, a written), fused it
+// moves 12 B and the first conv's whole kernel time disappears under the second's memory time.
+//
+// How: the first GEMM accumulates in TMEM; its epilogue applies bias + leaky_relu, rounds to bf16 and
+// writes the tile straight into shared memory in the swizzled K-major layout a UMMA descriptor
+// reads, so the second GEMM uses it as its A operand with the same tap-shifted descriptors.  A tile
+// computes MT = MS*128 rows of xt and keeps the R = MT - (k-1) output rows that have their full c2
+// footprint; tiles advance by R rows (96-98 % useful work).  Rows of xt outside [0,L) are forced to
+// zero — c2 zero-pads xt, it does not see c1 evaluated beyond the sequence.
+//
+// Pipeline per CTA (persistent, grid-strided tiles; D1, D2 and the slab double-buffered, xt single- or
+// double-buffered as shared memory allows):
+//     tensor pipe : G1(0) G1(1) G2(0) G1(2) G2(1) G1(3) G2(2) ...
+//     epilogue    : E1(0) E1(1) E2(0) E1(2) E2(1) ...
+//       E1 = TMEM -> bias, leaky_relu, bf16 -> xt tile in smem;  E2 = TMEM -> transpose -> residual -> HBM
+// Warp roles (608 threads): 0 weight producer | 1 MMA issuer + TMEM owner | 2 slab producer (TMA) |
+// 3..18 epilogue.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdio.h>
+
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace hg {
+
+constexpr int kPairEpiWarps = 16;
+constexpr int kPairThreads = (3 + kPairEpiWarps) * 32;
+constexpr int kPairStageFloats = 32 * 32;        // per-warp transpose tile: 32 rows x 32 fp32 columns
+
+template <int C, int MS>
+__global__ void __launch_bounds__(kPairThreads, 1)
+conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_res,
+                    const TcPairParams p) {
+  constexpr int KC = C, N_T = C;
+  constexpr int ROWB = KC * 2;
+  constexpr int STAGE_BYTES = N_T * ROWB;
+  constexpr int KSTEPS = KC / 16;
+  constexpr uint32_t ACC_COLS = MS * N_T;  // 128
+  constexpr uint32_t TMEM_COLS = 4 * ACC_COLS;
+  constexpr uint32_t SBO = 8 * ROWB;
+  constexpr uint32_t LAYOUT = (KC == 64) ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
+  static_assert(TMEM_COLS == 512, "four accumulator buffers of 128 columns");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int slab_bytes = p.slab_rows * ROWB;  // multiple of 1024 (host rounds the rows)
+  const int t_bytes = p.t_rows * ROWB;        // multiple of 1024
+  uint8_t* slab = smem;                       // [2][slab_bytes]
+  uint8_t* tbuf = slab + 2 * slab_bytes;      // [t_bufs][t_bytes]
+  float* staging = reinterpret_cast<float*>(tbuf + p.t_bufs * t_bytes);  // [16][4 KB], 1024-aligned (TMA dst)
+  uint8_t* wst = reinterpret_cast<uint8_t*>(staging + kPairEpiWarps * kPairStageFloats);  // [stages][STAGE_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wst + p.stages * STAGE_BYTES);
+  uint64_t* slab_full = bars;        // [2]
+  uint64_t* slab_empty = bars + 2;   // [2]
+  uint64_t* d1_full = bars + 4;      // [2]  G1 -> E1
+  uint64_t* d1_empty = bars + 6;     // [2]  E1 -> G1
+  uint64_t* t_full = bars + 8;       // [2]  E1 -> G2
+  uint64_t* t_empty = bars + 10;     // [2]  G2 -> E1
+  uint64_t* d2_full = bars + 12;     // [2]  G2 -> E2
+  uint64_t* d2_empty = bars + 14;    // [2]  E2 -> G2
+  uint64_t* res_bar = bars + 16;     // [16] residual tile landed in a warp's staging slot (TMA)
+  uint64_t* w_full = bars + 32;      // [stages]
+  uint64_t* w_empty = w_full + p.stages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_empty + p.stages);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h2 = (p.k - 1) >> 1;
+  const int p1 = p.d1 * h2;
+  // number of tiles this CTA owns
+  const int n_my = p.total_work > static_cast<int>(blockIdx.x)
+                       ? (p.total_work - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
+                       : 0;
+
+  if (warp == 0 && lane == 0) { prefetch_tensormap(&map_in); prefetch_tensormap(&map_res); }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&slab_full[i], 1); mbar_init(&slab_empty[i], 1);
+        mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], kPairEpiWarps);
+        mbar_init(&t_full[i], kPairEpiWarps); mbar_init(&t_empty[i], 1);
+        mbar_init(&d2_full[i], 1); mbar_init(&d2_empty[i], kPairEpiWarps);
+      }
+      for (int s = 0; s < p.stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+      for (int w = 0; w < kPairEpiWarps; ++w) mbar_init(&res_bar[w], 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------ weight producer: same order as the MMA issuer
+    if (lane == 0 && n_my > 0) {
+      int stage = 0; uint32_t phase = 0;
+      auto load_conv = [&](const uint8_t* w) {
+        for (int t = 0; t < p.k; ++t) {
+          mbar_wait(&w_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&w_full[stage], STAGE_BYTES);
+          bulk_load_1d(wst + stage * STAGE_BYTES, w + static_cast<size_t>(t) * STAGE_BYTES, STAGE_BYTES, &w_full[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      };
+      if (p.w_resident) {
+        load_conv(p.w1);
+        load_conv(p.w2);
+      } else {
+        load_conv(p.w1);                       // G1(0)
+        for (int i = 0; i < n_my; ++i) {
+          if (i + 1 < n_my) load_conv(p.w1);   // G1(i+1)
+          load_conv(p.w2);                     // G2(i)
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------ input slab producer (TMA)
+    if (lane == 0) {
+      for (int i = 0; i < n_my; ++i) {
+        const int work = blockIdx.x + i * gridDim.x;
+        const int b = work / p.tiles_per_item;
+        const int m0 = (work - b * p.tiles_per_item) * p.r_out;
+        const int buf = i & 1;
+        mbar_wait(&slab_empty[buf], ((i >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&slab_full[buf], slab_bytes);
+        uint8_t* dst = slab + buf * slab_bytes;
+        for (int bx = 0; bx < p.nboxes; ++bx)
+          tma_load_3d(dst + bx * p.box_rows * ROWB, &map_in, &slab_full[buf], 0, m0 - h2 - p1 + bx * p.box_rows, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16(128, N_T);
+    constexpr uint32_t desc_hi = ((SBO >> 4) & 0x3FFFu) | (1u << 14) | (LAYOUT << 29);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t slab_lo = (smem_u32(slab) & 0x3FFFFu) >> 4;
+    const uint32_t t_lo = (smem_u32(tbuf) & 0x3FFFFu) >> 4;
+    const uint32_t wst_lo = (smem_u32(wst) & 0x3FFFFu) >> 4;
+    int stage = 0; uint32_t wphase = 0;
+    bool w_seen = false;  // resident mode: every stage has been waited for once
+
+    // one GEMM: k taps, A = base + tap*row_step rows, accumulate into `acc`
+    auto gemm = [&](uint32_t a_base_lo, uint32_t tap_step_lo, uint32_t acc, int conv) {
+      for (int t = 0; t < p.k; ++t) {
+        const int st = p.w_resident ? conv * p.k + t : stage;
+        if (!p.w_resident || !w_seen) {
+          mbar_wait(&w_full[st], p.w_resident ? 0u : wphase);
+          tc_fence_after();
+        }
+        const uint32_t b_lo = wst_lo + static_cast<uint32_t>(st) * (STAGE_BYTES >> 4);
+        const uint32_t a_lo0 = a_base_lo + static_cast<uint32_t>(t) * tap_step_lo;
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < KSTEPS; ++ks) {
+#pragma unroll
+            for (int ms = 0; ms < MS; ++ms)
+              umma_bf16_lohi(acc + ms * N_T, a_lo0 + static_cast<uint32_t>(ms * ((128 * ROWB) >> 4) + ks * 2), b_lo + ks * 2,
+                             desc_hi, idesc, (ks == 0 && t == 0) ? 0u : 1u);
+          }
+          if (!p.w_resident) umma_commit(&w_empty[stage]);
+        }
+        __syncwarp();
+        if (!p.w_resident && ++stage == p.stages) { stage = 0; wphase ^= 1; }
+      }
+    };
+    auto g1 = [&](int i) {
+      const int buf = i & 1;
+      const uint32_t ph = (i >> 1) & 1;
+      mbar_wait(&d1_empty[buf], ph ^ 1);
+      mbar_wait(&slab_full[buf], ph);
+      tc_fence_after();
+      gemm(slab_lo + static_cast<uint32_t>(buf) * (static_cast<uint32_t>(slab_bytes) >> 4),
+           (static_cast<uint32_t>(p.d1) * ROWB) >> 4, tmem_u + buf * ACC_COLS, 0);
+      if (elect_one()) { umma_commit(&slab_empty[buf]); umma_commit(&d1_full[buf]); }
+      __syncwarp();
+    };
+    auto g2 = [&](int i) {
+      const int buf = i & 1;
+      const uint32_t ph = (i >> 1) & 1;
+      const int tbi = p.t_bufs == 2 ? buf : 0;
+      const uint32_t tph = p.t_bufs == 2 ? ph : static_cast<uint32_t>(i & 1);
+      mbar_wait(&t_full[tbi], tph);
+      mbar_wait(&d2_empty[buf], ph ^ 1);
+      tc_fence_after();
+      gemm(t_lo + static_cast<uint32_t>(tbi) * (static_cast<uint32_t>(t_bytes) >> 4), ROWB >> 4,
+           tmem_u + (2 + buf) * ACC_COLS, 1);
+      if (elect_one()) { umma_commit(&t_empty[tbi]); umma_commit(&d2_full[buf]); }
+      __syncwarp();
+    };
+    if (n_my > 0) g1(0);
+    for (int i = 0; i < n_my; ++i) {
+      if (i + 1 < n_my) g1(i + 1);
+      g2(i);
+      w_seen = true;
+    }
+  } else {
+    // ------------------------------------------------ epilogue warps (all 16 do E1 then E2)
+    const int e = warp - 3;
+    const int quarter = warp & 3;
+    const int sub = e >> 2;  // 0..3: which of the four warps sharing this TMEM lane quarter
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    float* stg = staging + e * kPairStageFloats;
+    const int c4 = lane & 7, rsub = lane >> 3;
+    // the one (sub-tile, 32-column) item of every tile this warp finishes in E2
+    constexpr int E2_CH = N_T / 32;
+    const int ms2 = sub / E2_CH, c02 = (sub - ms2 * E2_CH) * 32;
+    const int n2 = c02 + c4 * 4;
+
+    // E1: D1 -> (+b1, leaky_relu, bf16) -> xt tile in UMMA layout; two (sub-tile, 16-column) items
+    auto e1 = [&](int i) {
+      const int work = blockIdx.x + i * gridDim.x;
+      const int b = work / p.tiles_per_item;
+      const int m0 = (work - b * p.tiles_per_item) * p.r_out;
+      const int buf = i & 1;
+      const uint32_t ph = (i >> 1) & 1;
+      const int tbi = p.t_bufs == 2 ? buf : 0;
+      const uint32_t tph = p.t_bufs == 2 ? ph : static_cast<uint32_t>(i & 1);
+      mbar_wait(&d1_full[buf], ph);
+      mbar_wait(&t_empty[tbi], tph ^ 1);  // the G2 that last read this xt buffer has retired
+      tc_fence_after();
+      uint8_t* tb = tbuf + tbi * t_bytes;
+      const uint32_t tmem_acc = tmem_base + buf * ACC_COLS + lane_base;
+      constexpr int ITEMS = MS * (N_T / 16);
+#pragma unroll 1
+      for (int j = sub; j < ITEMS; j += 4) {
+        const int ms = j / (N_T / 16), c0 = (j - ms * (N_T / 16)) * 16;
+        uint32_t r[16];
+        tmem_ld_32x16(tmem_acc + ms * N_T + c0, r);
+        tmem_ld_wait();
+        if (j + 4 >= ITEMS) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&d1_empty[buf]);
+        }
+        const int row = ms * 128 + quarter * 32 + lane;  // row of the xt tile
+        const int grow = m0 - h2 + row;                  // global time index of that row
+        const bool inside = grow >= 0 && grow < p.L;
+        uint32_t pk[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 bb = *reinterpret_cast<const float4*>(p.bias1 + c0 + 4 * q);
+          const float v0 = inside ? lrelu_fast(__uint_as_float(r[4 * q]) + bb.x, p.slope) : 0.f;
+          const float v1 = inside ? lrelu_fast(__uint_as_float(r[4 * q + 1]) + bb.y, p.slope) : 0.f;
+          const float v2 = inside ? lrelu_fast(__uint_as_float(r[4 * q + 2]) + bb.z, p.slope) : 0.f;
+          const float v3 = inside ? lrelu_fast(__uint_as_float(r[4 * q + 3]) + bb.w, p.slope) : 0.f;
+          const uint2 u = pack_bf16x4(v0, v1, v2, v3);
+          pk[2 * q] = u.x; pk[2 * q + 1] = u.y;
+        }
+        const uint32_t swz = (KC == 64) ? (row & 7) : ((row >> 1) & 3);
+        const int ch = c0 >> 3;  // first 16-byte chunk of this item within the row
+        uint8_t* rp = tb + row * ROWB;
+        *reinterpret_cast<uint4*>(rp + (((ch) ^ swz) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(rp + (((ch + 1) ^ swz) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      fence_proxy_async();  // generic-proxy writes of xt -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_full[tbi]);
+    };
+
+    // E2: D2 + residual -> smem transpose -> fused epilogue of c2.  The fp32 residual tile of this
+    // warp's item is TMA-loaded straight into the warp's 4 KB staging slot (128B-swizzled box = the
+    // staging swizzle) a whole tile ahead, so no thread ever waits on a global load: the accumulator
+    // row is added to it in place, and after the transpose 8 lanes cover one 128-byte row segment.
+    auto coords = [&](int i, int& b, int& m0) {
+      const int work = blockIdx.x + i * gridDim.x;
+      b = work / p.tiles_per_item;
+      m0 = (work - b * p.tiles_per_item) * p.r_out;
+    };
+    auto prefetch_res = [&](int i) {  // lane 0 only
+      int b, m0;
+      coords(i, b, m0);
+      mbar_arrive_expect_tx(&res_bar[e], kPairStageFloats * 4);
+      tma_load_3d(stg, &map_res, &res_bar[e], c02, m0 + ms2 * 128 + quarter * 32, b);
+    };
+    auto e2 = [&](int i) {
+      int b, m0;
+      coords(i, b, m0);
+      const int buf = i & 1;
+      mbar_wait(&d2_full[buf], (i >> 1) & 1);
+      tc_fence_after();
+      {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (2 + buf) * ACC_COLS + lane_base + ms2 * N_T + c02, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&d2_empty[buf]);
+        mbar_wait(&res_bar[e], i & 1);
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          float4* sp = reinterpret_cast<float4*>(stg + lane * 32 + ((k4 ^ (lane & 7)) << 2));
+          float4 t = *sp;
+          t.x += __uint_as_float(r[4 * k4]); t.y += __uint_as_float(r[4 * k4 + 1]);
+          t.z += __uint_as_float(r[4 * k4 + 2]); t.w += __uint_as_float(r[4 * k4 + 3]);
+          *sp = t;
+        }
+      }
+      __syncwarp();
+      float v[8][4];
+#pragma unroll
+      for (int ii = 0; ii < 8; ++ii) {
+        const int row = ii * 4 + rsub;
+        const float4 t4 = *reinterpret_cast<const float4*>(stg + row * 32 + ((c4 ^ (row & 7)) << 2));
+        v[ii][0] = t4.x; v[ii][1] = t4.y; v[ii][2] = t4.z; v[ii][3] = t4.w;
+      }
+      fence_proxy_async();  // our generic reads of the slot happen-before the next TMA write into it
+      __syncwarp();
+      if (lane == 0 && i + 1 < n_my) prefetch_res(i + 1);
+      epilogue_rows<8>(p.epi, b, static_cast<long long>(m0) + ms2 * 128 + quarter * 32 + rsub, 4, n2, v,
+                       static_cast<long long>(m0) + p.r_out);
+    };
+    if (n_my > 0) {
+      if (lane == 0) prefetch_res(0);
+      e1(0);
+    }
+    for (int i = 0; i < n_my; ++i) {
+      if (i + 1 < n_my) e1(i + 1);
+      e2(i);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+size_t conv_pair_smem_bytes(int c, int slab_rows, int t_rows, int t_bufs, int stages) {
+  const int rowb = c * 2;
+  return 1024 + 2 * static_cast<size_t>(slab_rows) * rowb + static_cast<size_t>(t_bufs) * t_rows * rowb +
+         static_cast<size_t>(stages) * c * rowb + kPairEpiWarps * kPairStageFloats * 4 + (32 + 2 * stages) * 8 + 16;
+}
+
+template <int C, int MS>
+static cudaError_t launch_pair(const CUtensorMap& m, const CUtensorMap& mr, const TcPairParams& p, size_t smem, int grid,
+                               cudaStream_t st) {
+  auto kern = conv_pair_tc_kernel<C, MS>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kPairThreads, smem, st>>>(m, mr, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv_pair_tc(int c, const CUtensorMap& m, const CUtensorMap& mr, const TcPairParams& p, size_t smem,
+                                int grid, cudaStream_t st) {
+  if (c == 64) return launch_pair<64, 2>(m, mr, p, smem, grid, st);
+  if (c == 32) return launch_pair<32, 4>(m, mr, p, smem, grid, st);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace hg
