@@ -180,3 +180,24 @@ def test_full_size_cross_check_against_ffma():
         m.precision = "fp32"
         part = m(mel[3:4, :, :200]).cpu()
     assert max_abs(part.numpy(), cpu.numpy()) <= FP32_TOL
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
+def test_multi_gpu_sharding_matches_single_gpu():
+    """T7 on real GPUs: utterance sharding is bitwise exact, the NCCL halo exchange reproduces the
+    monolithic forward (tools/multi_gpu_check.py, one process per GPU)."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    n = min(torch.cuda.device_count(), 8)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29531",
+                        os.path.join(root, "tools", "multi_gpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    for prec in ("fp32", "bf16"):
+        assert res[prec]["utterance_sharding_bitwise_equal"]
+        assert res[prec]["long_form_max_abs_vs_single_gpu"] <= 1e-6

@@ -102,7 +102,7 @@ __device__ __forceinline__ uint2 pack_bf16x4(float a0, float a1, float a2, float
 // leaky_relu for 0 <= slope <= 1 in two instructions
 __device__ __forceinline__ float lrelu_fast(float v, float slope) { return fmaxf(v, v * slope); }
 
-template <int NR>
+template <int NR, bool WITH_RES = true>
 __device__ __forceinline__ void epilogue_rows(const EpiParams& e, int b, long long q0, int row_step, int n,
                                               float (&v)[NR][4], long long q_limit = 0x7fffffffffffffffLL) {
   const long long f0 = q0 * e.out_row_stride + n + e.out_offset;
@@ -115,7 +115,7 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& e, int b, long lo
     ok[i] = f >= 0 && f + 4 <= e.out_extent && q0 + static_cast<long long>(i) * row_step < q_limit;
   }
   const float4 bb = *reinterpret_cast<const float4*>(e.bias + n);
-  if (e.res) {
+  if (WITH_RES && e.res) {
     const float* rp = e.res + base + f0;
     float4 r[NR];
 #pragma unroll
@@ -129,14 +129,20 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& e, int b, long lo
 #pragma unroll
     for (int i = 0; i < NR; ++i) { v[i][0] += bb.x; v[i][1] += bb.y; v[i][2] += bb.z; v[i][3] += bb.w; }
   }
-  if (e.acc_in) {
+  if (e.acc_in) {  // MRF accumulate: 8 of 72 layers — loads in two batches to keep registers down
     const float* ap = e.acc_in + base + f0;
-    float4 r[NR];
 #pragma unroll
-    for (int i = 0; i < NR; ++i) r[i] = ok[i] ? *reinterpret_cast<const float4*>(ap + i * fstep) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int h = 0; h < NR; h += 4) {
+      float4 r[4];
 #pragma unroll
-    for (int i = 0; i < NR; ++i) {
-      v[i][0] = r[i].x + v[i][0]; v[i][1] = r[i].y + v[i][1]; v[i][2] = r[i].z + v[i][2]; v[i][3] = r[i].w + v[i][3];
+      for (int i = 0; i < 4; ++i)
+        r[i] = (h + i < NR && ok[h + i]) ? *reinterpret_cast<const float4*>(ap + (h + i) * fstep) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (h + i >= NR) continue;
+        v[h + i][0] = r[i].x + v[h + i][0]; v[h + i][1] = r[i].y + v[h + i][1];
+        v[h + i][2] = r[i].z + v[h + i][2]; v[h + i][3] = r[i].w + v[h + i][3];
+      }
     }
   }
   if (e.post_div > 0.f) {
@@ -331,6 +337,7 @@ struct TcConvParams {
   int w_resident;  // 1: every weight tile stays in shared memory for the CTA's lifetime
   int n_blocks;    // N tiles (grid-strided together with the M tiles)
   int total_work;  // B * tiles_per_item * n_blocks
+  int res_tma;     // 1: the fp32 residual is TMA-loaded into the epilogue staging slots (epi.res is null)
   int desc_mode;  // how a tap's row shift enters the UMMA descriptor (see conv_tc.cu)
   const uint8_t* w_hi;  // packed swizzled weight tiles [n_blk][chunk][tap][N_T rows][KC]
   const uint8_t* w_lo;

@@ -317,7 +317,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
       fence_proxy_async();  // our generic reads of the slot happen-before the next TMA write into it
       __syncwarp();
       if (lane == 0 && i + 1 < n_my) prefetch_res(i + 1);
-      epilogue_rows<8>(p.epi, b, static_cast<long long>(m0) + ms2 * 128 + quarter * 32 + rsub, 4, n2, v,
+      epilogue_rows<8, false>(p.epi, b, static_cast<long long>(m0) + ms2 * 128 + quarter * 32 + rsub, 4, n2, v,
                        static_cast<long long>(m0) + p.r_out);
     };
     if (n_my > 0) {
