@@ -15,9 +15,9 @@
 
 namespace hg {
 // kernels.cu-side launchers
-size_t conv_tc_smem_bytes(int n_t, int kc, bool split, int slab_rows, int nbuf, int stages);
-cudaError_t launch_conv_tc(int n_t, int kc, int ms, bool split, const CUtensorMap& mh, const CUtensorMap& ml,
-                           const TcConvParams& p, int n_blocks, size_t smem, int grid_ctas, cudaStream_t st);
+size_t conv_tc_smem_bytes(int n_t, int kc, bool split, int slab_rows, int nbuf, int stages, int epi_slot_bytes);
+cudaError_t launch_conv_tc(int n_t, int kc, int ms, bool split, const CUtensorMap* maps, const TcConvParams& p,
+                           int n_blocks, size_t smem, int grid_ctas, cudaStream_t st);
 cudaError_t launch_conv_ffma(const FfmaConvParams& p, cudaStream_t st);
 cudaError_t launch_conv_post(const float* x, int B, int L, int C, const float* w_tapmajor, float bias, float* out_f32,
                              int16_t* out_i16, float out_scale, cudaStream_t st);
@@ -129,10 +129,12 @@ static int make_operand_map(HgPlan* plan, const void* ptr, int L, int B, int cpi
   return HG_OK;
 }
 
-// fp32 tensor [B][L][C] -> 3-D map with a {32 channels, 32 rows, 1} box, 128B swizzle: the residual
-// tiles the fused-pair epilogue pulls straight into its staging slots.
-static int make_f32_tile_map(HgPlan* plan, const void* ptr, int L, int B, int c, CUtensorMap* out) {
-  MapKey key(ptr, L, B, c, -32, 32);
+// Epilogue tile maps over a channels-last tensor [B][L][C]: box {cols, 32 rows, 1}.
+//   kind 0: fp32, 32 columns, 128B swizzle  (fused-pair residual tiles)
+//   kind 1: fp32, 16 columns,  64B swizzle  (conv_tc residual in / x out)
+//   kind 2: bf16, 16 columns,  32B swizzle  (conv_tc operand copies out)
+static int make_tile_map(HgPlan* plan, const void* ptr, int L, int B, int c, int kind, CUtensorMap* out) {
+  MapKey key(ptr, L, B, c, -(kind + 1), 32);
   {
     std::lock_guard<std::mutex> g(plan->mu);
     auto it = plan->maps.find(key);
@@ -140,21 +142,27 @@ static int make_f32_tile_map(HgPlan* plan, const void* ptr, int L, int B, int c,
   }
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(HG_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  const int esz = kind == 2 ? 2 : 4;
+  const int cols = kind == 0 ? 32 : 16;
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(B)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(c) * 4, static_cast<cuuint64_t>(L) * c * 4};
-  cuuint32_t box[3] = {32, 32, 1};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(c) * esz, static_cast<cuuint64_t>(L) * c * esz};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(cols), 32, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMap m;
-  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(HG_ECUDA, "cuTensorMapEncodeTiled (fp32 tile) failed (%d)", static_cast<int>(r));
+  CUresult r = enc(&m, kind == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   kind == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : kind == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(HG_ECUDA, "cuTensorMapEncodeTiled (tile kind %d) failed (%d)", kind, static_cast<int>(r));
   {
     std::lock_guard<std::mutex> g(plan->mu);
     plan->maps[key] = m;
   }
   *out = m;
   return HG_OK;
+}
+static int make_f32_tile_map(HgPlan* plan, const void* ptr, int L, int B, int c, CUtensorMap* out) {
+  return make_tile_map(plan, ptr, L, B, c, 0, out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -230,6 +238,7 @@ extern "C" int hg_plan_create(const HgConfig* cfg, int device, HgPlan** out) {
   p->force_ffma = env_int("HG_FORCE_FFMA", 0) != 0;
   p->ctas_per_sm = env_int("HG_TC_CTAS_PER_SM", 1);
   p->fuse_pairs = env_int("HG_FUSE_PAIRS", 1) != 0;
+  p->epi_tma = env_int("HG_EPI_TMA", 1) != 0;
   const int uic = cfg->upsample_initial_channel;
   p->layers.push_back(make_conv("conv_pre", cfg->num_mels, uic, 7, 1));
   for (int i = 0; i < cfg->num_upsamples; ++i) {
@@ -423,7 +432,7 @@ static bool use_tc(const HgPlan* plan, const Layer& l, int precision) {
   return l.tc && precision != HG_PREC_FP32_FFMA && !plan->force_ffma;
 }
 
-static TcTiling choose_tiling(const HgPlan* plan, const Layer& l, bool split) {
+static TcTiling choose_tiling(const HgPlan* plan, const Layer& l, bool split, int slot = 6144) {
   TcTiling t;
   int min_off = l.tap_off[0], max_off = l.tap_off[0];
   for (int j = 1; j < l.ntaps; ++j) {
@@ -447,27 +456,27 @@ static TcTiling choose_tiling(const HgPlan* plan, const Layer& l, bool split) {
     t.stages = 0;
     // 1) weights resident for the CTA's lifetime (single N block only) with a double-buffered slab
     if (l.n_blocks == 1 && !plan->force_stages &&
-        conv_tc_smem_bytes(l.n_tile, l.kc, split, t.slab_rows, 2, total_stages) <= kMaxSmem) {
+        conv_tc_smem_bytes(l.n_tile, l.kc, split, t.slab_rows, 2, total_stages, slot) <= kMaxSmem) {
       t.resident = true;
       t.stages = total_stages;
       t.nbuf = 2;
-      if (conv_tc_smem_bytes(l.n_tile, l.kc, split, t.slab_rows, 3, total_stages) <= kMaxSmem) t.nbuf = 3;
+      if (conv_tc_smem_bytes(l.n_tile, l.kc, split, t.slab_rows, 3, total_stages, slot) <= kMaxSmem) t.nbuf = 3;
       break;
     }
     // 2) weights streamed through a ring: at least 3 stages next to a double-buffered slab
     t.resident = false;
     t.nbuf = 2;
     int s = 8;
-    while (s >= 2 && conv_tc_smem_bytes(l.n_tile, l.kc, split, t.slab_rows, t.nbuf, s) > kMaxSmem) --s;
+    while (s >= 2 && conv_tc_smem_bytes(l.n_tile, l.kc, split, t.slab_rows, t.nbuf, s, slot) > kMaxSmem) --s;
     if (plan->force_stages) s = plan->force_stages;
-    if (s >= 2 && conv_tc_smem_bytes(l.n_tile, l.kc, split, t.slab_rows, t.nbuf, s) <= kMaxSmem) {
+    if (s >= 2 && conv_tc_smem_bytes(l.n_tile, l.kc, split, t.slab_rows, t.nbuf, s, slot) <= kMaxSmem) {
       t.stages = s;
-      if (s >= 4 && conv_tc_smem_bytes(l.n_tile, l.kc, split, t.slab_rows, 3, s) <= kMaxSmem) t.nbuf = 3;
+      if (s >= 4 && conv_tc_smem_bytes(l.n_tile, l.kc, split, t.slab_rows, 3, s, slot) <= kMaxSmem) t.nbuf = 3;
       break;
     }
     if (ms == 1) break;  // does not fit at all -> CUDA-core path
   }
-  t.smem = conv_tc_smem_bytes(l.n_tile, l.kc, split, t.slab_rows, t.nbuf, t.stages);
+  t.smem = conv_tc_smem_bytes(l.n_tile, l.kc, split, t.slab_rows, t.nbuf, t.stages, slot);
   return t;
 }
 
@@ -484,7 +493,21 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
   epi.out_offset = l.kind == L_CONVT ? -static_cast<long long>(l.pad) * l.cout : 0;
   if (use_tc(plan, l, precision)) {
     const bool split = precision == HG_PREC_FP32;
-    TcTiling t = choose_tiling(plan, l, split);
+    // TMA epilogue for same-length convs without MRF accumulate (68 of the 78 layers of V1); its
+    // per-warp slot holds the residual-in, x-out and operand-out tiles the layer actually uses
+    bool tma_epi = plan->epi_tma && l.kind == L_CONV && !epi.acc_in && epi.post_div <= 0.f && l.cout % 16 == 0;
+    int slot = 2048;  // generic epilogue: one 32x16 fp32 transpose tile per warp
+    if (tma_epi) {
+      slot = (epi.res ? 2048 : 0) + (epi.out_x ? 2048 : 0) + (epi.out_a0 ? (split ? 2048 : 1024) : 0);
+      slot = std::max(slot, 1024);
+    }
+    TcTiling t = choose_tiling(plan, l, split, slot);
+    if (tma_epi && (t.stages < 3 && !t.resident)) {
+      // the TMA epilogue's tiles squeeze the weight ring too far (fp32 split mode at 256 channels):
+      // use the generic epilogue's 2 KB transpose slots instead
+      TcTiling t2 = choose_tiling(plan, l, split, 2048);
+      if (t2.stages > t.stages) { t = t2; tma_epi = false; slot = 2048; }
+    }
     if (t.stages >= 2) {
       TcConvParams p;
       memset(&p, 0, sizeof(p));
@@ -498,13 +521,42 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
       p.n_blocks = l.n_blocks;
       p.total_work = B * p.tiles_per_item * l.n_blocks;
       p.w_hi = l.w_hi; p.w_lo = l.w_lo; p.epi = epi;
-      CUtensorMap mh, ml;
-      int rc = make_operand_map(plan, in.a0, L_in, B, l.cin_pad, l.kc, t.box_rows, &mh);
+      CUtensorMap maps[6];
+      int rc = make_operand_map(plan, in.a0, L_in, B, l.cin_pad, l.kc, t.box_rows, &maps[0]);
       if (rc) return rc;
-      ml = mh;
-      if (split && (rc = make_operand_map(plan, in.a1, L_in, B, l.cin_pad, l.kc, t.box_rows, &ml))) return rc;
+      maps[1] = maps[0];
+      if (split && (rc = make_operand_map(plan, in.a1, L_in, B, l.cin_pad, l.kc, t.box_rows, &maps[1]))) return rc;
+      maps[2] = maps[3] = maps[4] = maps[5] = maps[0];
+      // TMA epilogue for same-length convs without MRF accumulate (68 of the 78 layers of V1)
+      p.epi_slot_bytes = slot;
+      if (tma_epi) {
+        p.epi_tma = 1;
+        if (epi.res) { p.has_res = 1; if ((rc = make_tile_map(plan, epi.res, L_in, B, l.cout, 1, &maps[2]))) return rc; }
+        if (epi.out_x) { p.has_x = 1; if ((rc = make_tile_map(plan, epi.out_x, L_in, B, l.cout, 1, &maps[3]))) return rc; }
+        if (epi.out_a0) {
+          p.has_a = 1;
+          if ((rc = make_tile_map(plan, epi.out_a0, L_in, B, l.cout, 2, &maps[4]))) return rc;
+          if (split && (rc = make_tile_map(plan, epi.out_a1, L_in, B, l.cout, 2, &maps[5]))) return rc;
+        }
+      }
       const int grid = std::min(p.total_work, plan->sm_count * std::max(1, plan->ctas_per_sm));
-      cudaError_t e = launch_conv_tc(l.n_tile, l.kc, t.ms, split, mh, ml, p, l.n_blocks, t.smem, grid, st);
+      static long long* dbg_buf = nullptr;
+      const char* dbg_layer = getenv("HG_TC_DEBUG_TIMING");  // layer name to instrument (bring-up only)
+      if (dbg_layer && l.name == dbg_layer) {
+        if (!dbg_buf) cudaMalloc(&dbg_buf, 256 * 8 * sizeof(long long));
+        cudaMemsetAsync(dbg_buf, 0, 256 * 8 * sizeof(long long), st);
+        p.dbg = dbg_buf;
+      }
+      cudaError_t e = launch_conv_tc(l.n_tile, l.kc, t.ms, split, maps, p, l.n_blocks, t.smem, grid, st);
+      if (p.dbg && e == cudaSuccess) {
+        std::vector<long long> h(256 * 8);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h.data(), dbg_buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        double tot = 0, a = 0, sl = 0, w = 0, n = 0;
+        for (int i = 0; i < grid; ++i) { tot += h[i * 8]; a += h[i * 8 + 1]; sl += h[i * 8 + 2]; w += h[i * 8 + 3]; n += h[i * 8 + 4]; }
+        fprintf(stderr, "[hg dbg] %s grid=%d tiles/cta=%.1f MMA-warp cycles: total=%.0f wait acc_empty=%.0f (%.1f%%) slab=%.0f (%.1f%%) weights=%.0f (%.1f%%)\n",
+                l.name.c_str(), grid, n / grid, tot / grid, a / grid, 100 * a / tot, sl / grid, 100 * sl / tot, w / grid, 100 * w / tot);
+      }
       if (e != cudaSuccess) return fail(HG_ECUDA, "conv_tc launch (%s): %s", l.name.c_str(), cudaGetErrorString(e));
       if (g_prof) prof_mark(static_cast<int>(&l - plan->layers.data()));
       return HG_OK;
@@ -876,6 +928,7 @@ static int op_layer(int device, int precision, Layer& l, const float* x, int B, 
   plan.force_stages = env_int("HG_TC_STAGES", 0);
   plan.force_ffma = env_int("HG_FORCE_FFMA", 0) != 0;
   plan.ctas_per_sm = env_int("HG_TC_CTAS_PER_SM", 1);
+  plan.epi_tma = env_int("HG_EPI_TMA", 1) != 0;
   {
     cudaDeviceProp pr;
     if (cudaGetDeviceProperties(&pr, device) == cudaSuccess) plan.sm_count = pr.multiProcessorCount;

@@ -337,8 +337,11 @@ struct TcConvParams {
   int w_resident;  // 1: every weight tile stays in shared memory for the CTA's lifetime
   int n_blocks;    // N tiles (grid-strided together with the M tiles)
   int total_work;  // B * tiles_per_item * n_blocks
-  int res_tma;     // 1: the fp32 residual is TMA-loaded into the epilogue staging slots (epi.res is null)
+  int epi_tma;     // 1: TMA epilogue (residual tiles loaded, x / operand tiles stored by TMA); 0: generic
+  int has_res, has_x, has_a;  // what the TMA epilogue reads / writes (maps are kernel arguments)
+  int epi_slot_bytes;         // shared memory per epilogue warp (TMA: res | x | a_hi | a_lo tiles; generic: 2 KB)
   int desc_mode;  // how a tap's row shift enters the UMMA descriptor (see conv_tc.cu)
+  long long* dbg;       // optional [grid][8] cycle counters (HG_TC_DEBUG_TIMING): MMA-warp wait breakdown
   const uint8_t* w_hi;  // packed swizzled weight tiles [n_blk][chunk][tap][N_T rows][KC]
   const uint8_t* w_lo;
   EpiParams epi;

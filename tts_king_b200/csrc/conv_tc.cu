@@ -50,6 +50,8 @@ __device__ __forceinline__ uint32_t desc_base_offset(uint32_t saddr, int desc_mo
 template <int N_T, int KC, int MS, bool SPLIT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+               const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_x,
+               const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
                const TcConvParams p) {
   constexpr int ROWB = KC * 2;                 // bytes per slab / weight row (= swizzle span)
   constexpr int PLANES = SPLIT ? 2 : 1;
@@ -65,14 +67,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int slab_bytes = p.slab_rows * ROWB;
   uint8_t* slab = smem;
-  uint8_t* wst = smem + ((p.nbuf * PLANES * slab_bytes + 1023) & ~1023);
-  float* staging = reinterpret_cast<float*>(wst + p.stages * STAGE_BYTES);  // [kEpiWarps][32*16]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kEpiWarps * kStageFloats);
+  // epilogue slots first (TMA sources / destinations want 1024-byte alignment), then the weight ring
+  uint8_t* epi_smem = smem + ((p.nbuf * PLANES * slab_bytes + 1023) & ~1023);  // [kEpiWarps][epi_slot_bytes]
+  float* staging = reinterpret_cast<float*>(epi_smem);                        // generic path: [kEpiWarps][32*16]
+  uint8_t* wst = epi_smem + kEpiWarps * p.epi_slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wst + p.stages * STAGE_BYTES);
   uint64_t* slab_full = bars;           // [4]
   uint64_t* slab_empty = bars + 4;      // [4]
   uint64_t* acc_full = bars + 8;        // [2]
   uint64_t* acc_empty = bars + 10;      // [2]
-  uint64_t* w_full = bars + 12;         // [stages]
+  uint64_t* res_bar = bars + 12;        // [16] residual tile landed in a warp's slot
+  uint64_t* w_full = bars + 28;         // [stages]
   uint64_t* w_empty = w_full + p.stages;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_empty + p.stages);
 
@@ -81,12 +86,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&map_hi);
     if (SPLIT) prefetch_tensormap(&map_lo);
+    if (p.epi_tma) {
+      if (p.has_res) prefetch_tensormap(&map_res);
+      if (p.has_x) prefetch_tensormap(&map_x);
+      if (p.has_a) { prefetch_tensormap(&map_ahi); if (SPLIT) prefetch_tensormap(&map_alo); }
+    }
   }
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < 4; ++i) { mbar_init(&slab_full[i], 1); mbar_init(&slab_empty[i], 1); }
       for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps); }
       for (int s = 0; s < p.stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+      for (int w = 0; w < kEpiWarps; ++w) mbar_init(&res_bar[w], 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -156,20 +167,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     int stage = 0; uint32_t wphase = 0;
     int buf = 0; uint32_t sphase = 0;
     int it = 0;
+    long long t_acc = 0, t_slab = 0, t_w = 0;
+    const long long t_begin = clock64();
     for (int work = blockIdx.x; work < p.total_work; work += gridDim.x, ++it) {
       const int ab = it & 1;
+      long long tq = clock64();
       mbar_wait(&acc_empty[ab], ((it >> 1) & 1) ^ 1);  // epilogue drained this accumulator buffer
+      t_acc += clock64() - tq;
       tc_fence_after();
       const uint32_t tmem_acc = tmem_u + ab * ACC_COLS;
       for (int c = 0; c < p.nc; ++c) {
+        tq = clock64();
         mbar_wait(&slab_full[buf], sphase);
+        t_slab += clock64() - tq;
         tc_fence_after();
         for (int t = 0; t < p.ntaps; ++t) {
           const uint32_t tap_lo = (static_cast<uint32_t>(p.tap_row[t]) * ROWB) >> 4;
 #pragma unroll
           for (int wp = 0; wp < PLANES; ++wp) {
             if (!p.w_resident || it == 0) {
+              tq = clock64();
               mbar_wait(&w_full[stage], wphase);
+              t_w += clock64() - tq;
               tc_fence_after();
             }
             const uint32_t b_lo = wst_lo + static_cast<uint32_t>(stage) * (STAGE_BYTES >> 4);
@@ -205,6 +224,143 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       if (elect_one()) umma_commit(&acc_full[ab]);
       __syncwarp();
     }
+    if (p.dbg && lane == 0) {
+      long long* d = p.dbg + static_cast<size_t>(blockIdx.x) * 8;
+      d[0] = clock64() - t_begin; d[1] = t_acc; d[2] = t_slab; d[3] = t_w; d[4] = it;
+    }
+  } else if (p.epi_tma) {
+    // ------------------------------------------------ TMA epilogue (same-length convs without MRF accumulate)
+    // Row-per-thread all the way: tcgen05.ld hands each thread one row of a (32 rows x 16 columns)
+    // item.  The fp32 residual tile of the warp's NEXT item is always in flight: it is TMA-loaded into
+    // the warp's `res` buffer as soon as the current item's residual has been read into registers.
+    // Results are written row-wise into separate `x` / `a` buffers (swizzled so that both the TMA box
+    // and the per-thread rows are bank-conflict free) and leave with TMA stores; the buffers are only
+    // reclaimed (wait_group.read) right before the next item overwrites them.  No LSU global access,
+    // no address arithmetic, no transpose; rows past the end of the sequence are clipped by TMA.
+    const int e = warp - 3;
+    const int quarter = warp & 3;
+    const int sub = e >> 2;
+    uint8_t* slot = epi_smem + e * p.epi_slot_bytes;
+    const float* rb = reinterpret_cast<const float*>(slot);                         // residual in (2 KB)
+    float* xb = reinterpret_cast<float*>(slot + (p.has_res ? 2048 : 0));             // x out (2 KB)
+    uint8_t* ab_hi = reinterpret_cast<uint8_t*>(xb) + (p.has_x ? 2048 : 0);          // operand copy out (1 KB)
+    uint8_t* ab_lo = ab_hi + 1024;
+    constexpr int ITEMS = MS * CHUNKS;
+    auto tile_coords = [&](int work, int& nblk, int& b, int& m0) {
+      nblk = work % p.n_blocks;
+      const int mt = work / p.n_blocks;
+      b = mt / p.tiles_per_item;
+      m0 = (mt - b * p.tiles_per_item) * (MS * 128);
+    };
+    auto prefetch_res = [&](int work, int j) {  // lane 0 only
+      int nblk, b, m0;
+      tile_coords(work, nblk, b, m0);
+      const int ms = j / CHUNKS, c0 = (j - ms * CHUNKS) * 16;
+      mbar_arrive_expect_tx(&res_bar[e], 2048);
+      tma_load_3d(slot, &map_res, &res_bar[e], nblk * N_T + c0, m0 + ms * 128 + quarter * 32, b);
+    };
+    uint32_t res_uses = 0;
+    if (p.has_res && lane == 0 && sub < ITEMS && static_cast<int>(blockIdx.x) < p.total_work) prefetch_res(blockIdx.x, sub);
+    const uint32_t swz64 = (lane >> 1) & 3, swz32 = (lane >> 2) & 1;
+    int it = 0;
+    for (int work = blockIdx.x; work < p.total_work; work += gridDim.x, ++it) {
+      int nblk, b, m0;
+      tile_coords(work, nblk, b, m0);
+      const int ab = it & 1;
+      const uint32_t tmem_acc = tmem_base + ab * ACC_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
+      mbar_wait(&acc_full[ab], (it >> 1) & 1);
+      tc_fence_after();
+      bool released = false;
+#pragma unroll 1
+      for (int j = sub; j < ITEMS; j += 4) {
+        const int ms = j / CHUNKS, c0 = (j - ms * CHUNKS) * 16;
+        const int n0 = nblk * N_T + c0;
+        float v[16];
+        {
+          uint32_t r[16];
+          tmem_ld_32x16(tmem_acc + ms * N_T + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+        }
+        if (j + 4 >= ITEMS) {  // last TMEM read of this warp for this tile: hand the buffer back early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[ab]);
+          released = true;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 bb = *reinterpret_cast<const float4*>(p.epi.bias + n0 + 4 * q);
+          v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
+        }
+        if (p.has_res) {
+          mbar_wait(&res_bar[e], res_uses & 1);
+          ++res_uses;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 t = *reinterpret_cast<const float4*>(rb + lane * 16 + ((q ^ swz64) << 2));
+            v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+          }
+          fence_proxy_async();  // our reads of the residual buffer happen-before the next TMA write into it
+          __syncwarp();
+          if (lane == 0) {       // next item's residual goes in flight now, a whole item ahead of its use
+            if (j + 4 < ITEMS) prefetch_res(work, j + 4);
+            else if (work + static_cast<int>(gridDim.x) < p.total_work) prefetch_res(work + gridDim.x, sub);
+          }
+        }
+        // reclaim the output buffers: the previous item's TMA stores must have finished reading them
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+        if (p.has_x) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(xb + lane * 16 + ((q ^ swz64) << 2)) =
+                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+        if (p.has_a) {
+          const float sl = p.epi.slope;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = lrelu_fast(v[i], sl);
+          uint32_t hi[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+            hi[q] = *reinterpret_cast<const uint32_t*>(&h);
+            if (SPLIT) { v[2 * q] -= __low2float(h); v[2 * q + 1] -= __high2float(h); }
+          }
+          *reinterpret_cast<uint4*>(ab_hi + lane * 32 + ((0 ^ swz32) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(ab_hi + lane * 32 + ((1 ^ swz32) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          if (SPLIT) {
+            uint32_t lo[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+              lo[q] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(ab_lo + lane * 32 + ((0 ^ swz32) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4*>(ab_lo + lane * 32 + ((1 ^ swz32) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+          }
+        }
+        fence_proxy_async();  // generic-proxy writes of the tiles -> visible to the TMA unit
+        __syncwarp();
+        if (lane == 0) {
+          const int row0 = m0 + ms * 128 + quarter * 32;
+          if (p.has_x) tma_store_3d(&map_x, xb, n0, row0, b);
+          if (p.has_a) {
+            tma_store_3d(&map_ahi, ab_hi, n0, row0, b);
+            if (SPLIT) tma_store_3d(&map_alo, ab_lo, n0, row0, b);
+          }
+          tma_store_commit();
+        }
+      }
+      if (!released) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[ab]);
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
   } else {
     // ------------------------------------------------ epilogue: TMEM -> regs -> smem transpose -> HBM
     // Warp e (0..15) may only touch TMEM lanes [32*(warp%4), +32).  The four warps that share a lane
@@ -275,15 +431,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 // host side
 
-size_t conv_tc_smem_bytes(int n_t, int kc, bool split, int slab_rows, int nbuf, int stages) {
+size_t conv_tc_smem_bytes(int n_t, int kc, bool split, int slab_rows, int nbuf, int stages, int epi_slot_bytes) {
   const int rowb = kc * 2, planes = split ? 2 : 1;
   size_t slab = (static_cast<size_t>(nbuf) * planes * slab_rows * rowb + 1023) & ~size_t(1023);
-  return 1024 + slab + static_cast<size_t>(stages) * n_t * rowb + kEpiWarps * kStageFloats * 4 + (12 + 2 * stages) * 8 + 16;
+  return 1024 + slab + static_cast<size_t>(stages) * n_t * rowb + static_cast<size_t>(kEpiWarps) * epi_slot_bytes +
+         (28 + 2 * stages) * 8 + 16;
 }
 
 template <int N_T, int KC, int MS, bool SPLIT>
-static cudaError_t launch_one(const CUtensorMap& mh, const CUtensorMap& ml, const TcConvParams& p, int n_blocks,
-                              size_t smem, int grid_ctas, cudaStream_t st) {
+static cudaError_t launch_one(const CUtensorMap* maps, const TcConvParams& p, int n_blocks, size_t smem, int grid_ctas,
+                              cudaStream_t st) {
   auto kern = conv_tc_kernel<N_T, KC, MS, SPLIT>;
   static size_t configured = 0;  // per-instantiation high-water mark
   if (smem > configured) {
@@ -292,22 +449,23 @@ static cudaError_t launch_one(const CUtensorMap& mh, const CUtensorMap& ml, cons
     configured = smem;
   }
   (void)n_blocks;
-  kern<<<grid_ctas, kTcThreads, smem, st>>>(mh, ml, p);
+  kern<<<grid_ctas, kTcThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
   return cudaGetLastError();
 }
 
 template <int N_T, int KC, int MS>
-static cudaError_t launch_split(bool split, const CUtensorMap& mh, const CUtensorMap& ml, const TcConvParams& p,
-                                int n_blocks, size_t smem, int grid_ctas, cudaStream_t st) {
-  return split ? launch_one<N_T, KC, MS, true>(mh, ml, p, n_blocks, smem, grid_ctas, st)
-               : launch_one<N_T, KC, MS, false>(mh, ml, p, n_blocks, smem, grid_ctas, st);
+static cudaError_t launch_split(bool split, const CUtensorMap* maps, const TcConvParams& p, int n_blocks, size_t smem,
+                                int grid_ctas, cudaStream_t st) {
+  return split ? launch_one<N_T, KC, MS, true>(maps, p, n_blocks, smem, grid_ctas, st)
+               : launch_one<N_T, KC, MS, false>(maps, p, n_blocks, smem, grid_ctas, st);
 }
 
 // Valid (N_T, KC, MS): N_T in {32,64,128,256}, KC in {32,64}, MS in {1,2,4}, 2*MS*N_T <= 512.
-cudaError_t launch_conv_tc(int n_t, int kc, int ms, bool split, const CUtensorMap& mh, const CUtensorMap& ml,
-                           const TcConvParams& p, int n_blocks, size_t smem, int grid_ctas, cudaStream_t st) {
+// maps: [0] operand hi, [1] operand lo, [2] residual (fp32), [3] x out (fp32), [4] a_hi out, [5] a_lo out
+cudaError_t launch_conv_tc(int n_t, int kc, int ms, bool split, const CUtensorMap* maps, const TcConvParams& p,
+                           int n_blocks, size_t smem, int grid_ctas, cudaStream_t st) {
 #define HG_CASE(NT, KCV, MSV) \
-  if (n_t == NT && kc == KCV && ms == MSV) return launch_split<NT, KCV, MSV>(split, mh, ml, p, n_blocks, smem, grid_ctas, st);
+  if (n_t == NT && kc == KCV && ms == MSV) return launch_split<NT, KCV, MSV>(split, maps, p, n_blocks, smem, grid_ctas, st);
   HG_CASE(256, 64, 1)
   HG_CASE(128, 64, 1) HG_CASE(128, 64, 2)
   HG_CASE(64, 64, 1) HG_CASE(64, 64, 2) HG_CASE(64, 64, 4)

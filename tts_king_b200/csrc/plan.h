@@ -60,6 +60,7 @@ struct HgPlan {
   int force_ms = 0, force_stages = 0;
   int ctas_per_sm = 1;  // persistent grid = min(work, SMs * ctas_per_sm)
   bool fuse_pairs = true;  // HG_FUSE_PAIRS=0: never use the fused ResBlock-pair kernel
+  bool epi_tma = true;     // HG_EPI_TMA=0: always use the generic (LSU) epilogue in conv_tc
   bool force_ffma = false;  // HG_FORCE_FFMA=1: route every layer to the CUDA-core kernel
   std::mutex mu;
   std::map<hg::MapKey, CUtensorMap> maps;
