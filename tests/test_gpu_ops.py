@@ -124,11 +124,11 @@ def test_conv_transpose1d_parity(cin, cout, k, s, prec):
     assert (y.double() - ref).abs().max().item() <= TOL[prec] * ref.abs().max().item()
 
 
-@pytest.mark.parametrize("C", [32, 8, 2])
+@pytest.mark.parametrize("C", [32, 64, 8, 2])
 def test_conv_post_parity(C):
     L = _native.lib()
     g = torch.Generator().manual_seed(C)
-    B, n = 3, 777
+    B, n = 3, 777  # 777 = 3 tiles of 256 + 9: ragged last tile
     x = torch.randn(B, C, n, generator=g)
     w = torch.randn(1, C, 7, generator=g) / (7 * C) ** 0.5
     b = torch.randn(1, generator=g)

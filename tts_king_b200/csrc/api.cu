@@ -20,7 +20,7 @@ cudaError_t launch_conv_tc(int n_t, int kc, int ms, bool split, const CUtensorMa
                            int n_blocks, size_t smem, int grid_ctas, cudaStream_t st);
 cudaError_t launch_conv_ffma(const FfmaConvParams& p, cudaStream_t st);
 cudaError_t launch_conv_post(const float* x, int B, int L, int C, const float* w_tapmajor, float bias, float* out_f32,
-                             int16_t* out_i16, float out_scale, cudaStream_t st);
+                             int16_t* out_i16, float out_scale, cudaStream_t st, const float* w_host_tapmajor);
 cudaError_t launch_mel_to_operand(const float* mel, long long sB, long long sC, long long sT, int B, int C, int T,
                                   int c_pad, int a_fmt, void* a0, void* a1, cudaStream_t st);
 cudaError_t launch_f32_to_operand(const float* x, long long n, float slope, int a_fmt, void* a0, void* a1,
@@ -322,6 +322,7 @@ static int pack_layer(Layer& l, const float* W, const float* bias) {
     for (int j = 0; j < l.k; ++j)
       for (int c = 0; c < l.cin; ++c) wp[static_cast<size_t>(j) * l.cin + c] = W[static_cast<size_t>(c) * l.k + j];
     if ((rc = upload(wp.data(), wp.size() * 4, reinterpret_cast<void**>(&l.w_post)))) return rc;
+    l.w_post_host = wp;
     l.bias_post = bias[0];
     l.loaded = true;
     return HG_OK;
@@ -852,7 +853,8 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
   const Layer& post = plan->layers.back();
   e = launch_conv_post(x_final, B, L, post.cin, post.w_post, post.bias_post,
                        out_dtype == HG_OUT_F32 ? static_cast<float*>(out) : nullptr,
-                       out_dtype == HG_OUT_I16 ? static_cast<int16_t*>(out) : nullptr, out_scale, st);
+                       out_dtype == HG_OUT_I16 ? static_cast<int16_t*>(out) : nullptr, out_scale, st,
+                       post.w_post_host.empty() ? nullptr : post.w_post_host.data());
   if (e != cudaSuccess) return fail(HG_ECUDA, "conv_post: %s", cudaGetErrorString(e));
   prof_mark(static_cast<int>(plan->layers.size()) - 1);
   return HG_OK;
@@ -988,7 +990,8 @@ extern "C" int hg_op_conv_post(int device, const float* x, int B, int L, int C, 
   l.name = "op.conv_post"; l.kind = L_POST; l.cin = C; l.cout = 1; l.k = 7; l.pad = 3;
   if ((rc = pack_layer(l, weight, bias))) { free_layer(l); return rc; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t e = launch_conv_post(x, B, L, C, l.w_post, l.bias_post, y, nullptr, 1.f, st);
+  cudaError_t e = launch_conv_post(x, B, L, C, l.w_post, l.bias_post, y, nullptr, 1.f, st,
+                                   l.w_post_host.empty() ? nullptr : l.w_post_host.data());
   cudaError_t es = cudaStreamSynchronize(st);
   free_layer(l);
   if (e != cudaSuccess) return fail(HG_ECUDA, "conv_post: %s", cudaGetErrorString(e));

@@ -36,6 +36,7 @@ struct Layer {
   float* w_ffma = nullptr;   // [tap][cin][n_total]
   float* bias = nullptr;     // [n_total] (bias[n % cout]); conv_post: host scalar below
   float* w_post = nullptr;   // conv_post: [7][C]
+  std::vector<float> w_post_host;  // same, host copy (passed by value in the kernel-parameter bank when C = 32)
   float bias_post = 0.f;
 };
 

@@ -80,9 +80,92 @@ __global__ void __launch_bounds__(kPostTile) conv_post_kernel(const float* __res
   }
 }
 
+// V1 fast path (C = 32).  The generic kernel above re-reads every staged row seven times (once per
+// tap) and is bound by shared-memory bandwidth (ncu: 1.9 TB/s of HBM).  Here each staged row is read
+// ONCE: its owner thread forms the seven per-tap partial dot products against weights that live in
+// the kernel-parameter constant bank (no loads at all), parks them in a small padded tile, and each
+// output sample is then the sum of seven partials from neighbouring rows.
+struct PostW32 {
+  float w[kPostK][32];
+};
+
+__global__ void __launch_bounds__(kPostTile) conv_post32_kernel(const float* __restrict__ x, int L, const PostW32 W,
+                                                                float bias, int tiles_per_item, float* __restrict__ out_f32,
+                                                                int16_t* __restrict__ out_i16, float out_scale) {
+  constexpr int C = 32, ROWS = kPostTile + kPostK - 1, PITCH = C + 4, PP = 9;
+  __shared__ __align__(16) float xs[ROWS * PITCH];
+  __shared__ float ps[ROWS * PP];
+  const int b = blockIdx.x / tiles_per_item;
+  const int t0 = (blockIdx.x - b * tiles_per_item) * kPostTile;
+  const float* xb = x + static_cast<long long>(b) * L * C;
+  // stage the window: all of a thread's loads are issued before the first is consumed (the rolled
+  // loop had one 16-byte load in flight per thread and ran at 2 TB/s, latency-bound)
+  constexpr int NV = ROWS * (C / 4);            // float4 elements in the window (2096)
+  constexpr int FULL = NV / kPostTile;          // 8 unrolled rounds ...
+  float4 v[FULL + 1];
+#pragma unroll
+  for (int i = 0; i <= FULL; ++i) {
+    const int e = threadIdx.x + i * kPostTile;  // ... plus a 48-element tail round
+    const int r = e >> 3, cc = (e & 7) << 2;
+    const int row = t0 - 3 + r;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e < NV && row >= 0 && row < L) v[i] = *reinterpret_cast<const float4*>(xb + static_cast<long long>(row) * C + cc);
+  }
+#pragma unroll
+  for (int i = 0; i <= FULL; ++i) {
+    const int e = threadIdx.x + i * kPostTile;
+    if (e < NV) {
+      const int r = e >> 3, cc = (e & 7) << 2;
+      float4 t = v[i];
+      t.x = lrelu(t.x, 0.01f); t.y = lrelu(t.y, 0.01f); t.z = lrelu(t.z, 0.01f); t.w = lrelu(t.w, 0.01f);
+      *reinterpret_cast<float4*>(xs + r * PITCH + cc) = t;
+    }
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < ROWS; r += kPostTile) {
+    float p[kPostK];
+#pragma unroll
+    for (int j = 0; j < kPostK; ++j) p[j] = 0.f;
+#pragma unroll
+    for (int c4 = 0; c4 < C / 4; ++c4) {
+      const float4 a = *reinterpret_cast<const float4*>(xs + r * PITCH + 4 * c4);
+#pragma unroll
+      for (int j = 0; j < kPostK; ++j) {
+        p[j] = fmaf(a.x, W.w[j][4 * c4], p[j]);
+        p[j] = fmaf(a.y, W.w[j][4 * c4 + 1], p[j]);
+        p[j] = fmaf(a.z, W.w[j][4 * c4 + 2], p[j]);
+        p[j] = fmaf(a.w, W.w[j][4 * c4 + 3], p[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kPostK; ++j) ps[r * PP + j] = p[j];
+  }
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  if (t >= L) return;
+  float acc = bias;
+#pragma unroll
+  for (int j = 0; j < kPostK; ++j) acc += ps[(threadIdx.x + j) * PP + j];
+  const float y = tanhf(acc);
+  const long long o = static_cast<long long>(b) * L + t;
+  if (out_f32) out_f32[o] = y;
+  if (out_i16) {
+    const int v = __float2int_rz(y * out_scale);
+    out_i16[o] = static_cast<int16_t>(static_cast<uint16_t>(static_cast<uint32_t>(v) & 0xFFFFu));
+  }
+}
+
 cudaError_t launch_conv_post(const float* x, int B, int L, int C, const float* w_tapmajor, float bias,
-                             float* out_f32, int16_t* out_i16, float out_scale, cudaStream_t st) {
+                             float* out_f32, int16_t* out_i16, float out_scale, cudaStream_t st,
+                             const float* w_host_tapmajor) {
   const int tiles = (L + kPostTile - 1) / kPostTile;
+  if (C == 32 && w_host_tapmajor) {
+    PostW32 W;
+    for (int j = 0; j < kPostK; ++j)
+      for (int c = 0; c < 32; ++c) W.w[j][c] = w_host_tapmajor[j * 32 + c];
+    conv_post32_kernel<<<static_cast<unsigned>(B * tiles), kPostTile, 0, st>>>(x, L, W, bias, tiles, out_f32, out_i16, out_scale);
+    return cudaGetLastError();
+  }
   const bool vec = (C & 3) == 0;
   const int pitch = vec ? C + 4 : C + 1;
   const size_t smem = (static_cast<size_t>(kPostTile + kPostK - 1) * pitch + kPostK * C) * sizeof(float);
