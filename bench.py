@@ -281,8 +281,16 @@ def main():
         mult = 3.0 if args.precision == "fp32" else 1.0  # bf16x3: compensation passes are overhead, not credited
         peak = float(peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"]))
         ach = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+        traffic = None  # DRAM bytes of the tcgen05 launches of one step, from the committed ncu launch list
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", f"traffic_{args.precision}.json")))
+            traffic = tj["tcgen05_kernels"]["dram_bytes_per_step"]
+        except Exception:
+            pass
         roofline = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "traffic": None, "kernel": "conv_tc_kernel + conv_pair_tc_kernel (tcgen05 implicit-GEMM convs, all launches)",
+                    "traffic": traffic, "traffic_note": "DRAM bytes per step summed over the tcgen05 launches (ncu), not per launch",
+                    "hbm_floor_ms": (traffic / (float(peaks.get("hbm_gbs", 6555.8)) * 1e9) * 1e3) if traffic else None,
+                    "tensor_floor_ms": tc_flops / (peak * 1e12) * 1e3, "measured_ms": tc_ms, "kernel": "conv_tc_kernel + conv_pair_tc_kernel (tcgen05 implicit-GEMM convs, all launches)",
                     "share_of_step": tc_ms / all_ms if all_ms else None, "peak_source": peaks["_source"] + " sustained bf16",
                     "mma_passes_per_product": mult}
         layers_out = rows
