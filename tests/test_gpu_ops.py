@@ -87,6 +87,24 @@ def test_conv1d_lengths(n, prec):
     assert (y.double() - ref).abs().max().item() <= TOL[prec] * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("prec", ["fp32_ffma", "fp32", "bf16"])
+@pytest.mark.parametrize("C,k,d,n", [(16, 3, 1, 700), (16, 11, 5, 513), (16, 7, 3, 1), (8, 3, 5, 1025), (8, 11, 5, 300),
+                                     (8, 7, 1, 511)])
+def test_narrow_conv1d_parity(C, k, d, n, prec):
+    """The CUDA-core kernel of the 16- / 8-channel stages (conv_narrow.cu, BASELINE cfg-4): exact fp32
+    arithmetic on whatever operand format the mode stores."""
+    g = torch.Generator().manual_seed(C * 100 + k * 10 + d)
+    x = torch.randn(2, C, n, generator=g)
+    w = torch.randn(C, C, k, generator=g) / (C * k) ** 0.5
+    b = torch.randn(C, generator=g) * 0.1
+    res = torch.randn(2, C, n, generator=g)
+    y = run_conv1d(x, w, b, d, 0.1, res, prec)
+    a = operand_model(F.leaky_relu(x, 0.1), prec)  # activations are stored in the mode's format; weights stay fp32
+    ref = F.conv1d(a, w.double(), b.double(), dilation=d, padding=(k * d - d) // 2) + res.double()
+    assert not torch.isnan(y).any()
+    assert (y.double() - ref).abs().max().item() <= 2e-6 * max(1.0, ref.abs().max().item())
+
+
 def test_conv1d_fp32_mode_is_fp32_accurate():
     """HG_PREC_FP32 (bf16x3) against the true fp64 result of the fp32 inputs — the accuracy the
     north_star's 1e-4 end-to-end bound rests on."""

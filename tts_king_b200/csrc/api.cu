@@ -26,6 +26,7 @@ cudaError_t launch_mel_to_operand(const float* mel, long long sB, long long sC, 
 cudaError_t launch_f32_to_operand(const float* x, long long n, float slope, int a_fmt, void* a0, void* a1,
                                   cudaStream_t st);
 int run_tcgen05_selftest(char* buf, size_t len);
+cudaError_t launch_conv_narrow(int c, NarrowConvParams p, cudaStream_t st);
 size_t conv_pair_smem_bytes(int c, int slab_rows, int t_rows, int t_bufs, int stages);
 cudaError_t launch_conv_pair_tc(int c, const CUtensorMap& m, const CUtensorMap& mr, const TcPairParams& p, size_t smem,
                                 int grid, cudaStream_t st);
@@ -562,6 +563,18 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
       if (g_prof) prof_mark(static_cast<int>(&l - plan->layers.data()));
       return HG_OK;
     }
+  }
+  // very narrow same-length convs (V2-style 16- / 8-channel stages): dedicated CUDA-core kernel
+  if (l.kind == L_CONV && l.cin == l.cout && (l.cin == 8 || l.cin == 16) && (l.k & 1) && !plan->force_ffma) {
+    NarrowConvParams np;
+    memset(&np, 0, sizeof(np));
+    np.B = B; np.L = L_in; np.k = l.k; np.dil = l.dil;
+    np.a0 = in.a0; np.a1 = in.a1; np.a_fmt = a_fmt_of(precision);
+    np.w = l.w_ffma; np.epi = epi;
+    cudaError_t e = launch_conv_narrow(l.cin, np, st);
+    if (e != cudaSuccess) return fail(HG_ECUDA, "conv_narrow launch (%s): %s", l.name.c_str(), cudaGetErrorString(e));
+    if (g_prof) prof_mark(static_cast<int>(&l - plan->layers.data()));
+    return HG_OK;
   }
   FfmaConvParams f;
   memset(&f, 0, sizeof(f));

@@ -383,4 +383,14 @@ struct FfmaConvParams {
   EpiParams epi;
 };
 
+// ------------------------------------------------------------------ narrow CUDA-core conv (C = 8 / 16)
+struct NarrowConvParams {
+  int B, L, k, dil, tiles_per_item;
+  const void* a0;   // operand planes [B][L][C]
+  const void* a1;
+  int a_fmt;
+  const float* w;   // [k][C_in][C_out]  (the CUDA-core weight layout of plan.h)
+  EpiParams epi;
+};
+
 }  // namespace hg
