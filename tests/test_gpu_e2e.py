@@ -182,6 +182,26 @@ def test_full_size_cross_check_against_ffma():
     assert max_abs(part.numpy(), cpu.numpy()) <= FP32_TOL
 
 
+def test_cuda_graph_replay_matches_eager():
+    """Graph-captured forward (the cfg-1 latency path): bit-identical to the eager launch sequence,
+    also for a non-contiguous input and after the weights' workspace has been reused."""
+    g = golden("v1_seed1234")
+    m = make_generator(fx.V1, precision="fp32").cuda()
+    mel = torch.from_numpy(g["mel_a"]).cuda()
+    with torch.no_grad():
+        eager = m(mel).clone()
+    run = m.make_graphed(1, mel.shape[-1])
+    y1 = run(mel).clone()
+    y2 = run(mel.transpose(1, 2).contiguous().transpose(1, 2)).clone()
+    with torch.no_grad():
+        m(fx.synthetic_mel(2, 50, seed=1).cuda())  # an unrelated eager call in between
+    y3 = run(mel).clone()
+    assert torch.equal(y1, eager) and torch.equal(y2, eager) and torch.equal(y3, eager)
+    assert max_abs(y1.cpu().numpy(), g["y_a"]) <= FP32_TOL
+    with pytest.raises(RuntimeError):
+        run(torch.zeros(1, 80, 7, device="cuda"))
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
 def test_multi_gpu_sharding_matches_single_gpu():
     """T7 on real GPUs: utterance sharding is bitwise exact, the NCCL halo exchange reproduces the

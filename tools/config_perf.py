@@ -38,5 +38,18 @@ for name, cfg, B, T in cases:
             e1.record()
             torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        print(json.dumps({"config": name, "precision": prec, "ms": ms, "audio_sec_per_sec": B * T * hop / 22050 / (ms * 1e-3),
-                          "launches": m.kernel_launches(B, T)}))
+        rec = {"config": name, "precision": prec, "ms": ms, "audio_sec_per_sec": B * T * hop / 22050 / (ms * 1e-3),
+               "launches": m.kernel_launches(B, T)}
+        if B * T <= 1024:  # latency regime: also time the CUDA-graph replay
+            run = m.make_graphed(B, T)
+            for _ in range(3):
+                run(mel)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                run(mel)
+            e1.record()
+            torch.cuda.synchronize()
+            rec["ms_cuda_graph"] = e0.elapsed_time(e1) / reps
+            rec["audio_sec_per_sec_cuda_graph"] = B * T * hop / 22050 / (rec["ms_cuda_graph"] * 1e-3)
+        print(json.dumps(rec))

@@ -100,6 +100,9 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // programmatic dependent launch: setup and the first weight stages overlap the previous layer's tail
+  pdl_launch_dependents();
+  if (warp != 0) pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------ weight producer: same order as the MMA issuer
@@ -348,8 +351,17 @@ static cudaError_t launch_pair(const CUtensorMap& m, const CUtensorMap& mr, cons
   auto kern = conv_pair_tc_kernel<C, MS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
-  kern<<<grid, kPairThreads, smem, st>>>(m, mr, p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(kPairThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, m, mr, p);
 }
 
 cudaError_t launch_conv_pair_tc(int c, const CUtensorMap& m, const CUtensorMap& mr, const TcPairParams& p, size_t smem,

@@ -108,6 +108,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
+  // prefetch) and the weight producer's first stages overlap the previous layer's tail; activations,
+  // residuals and outputs are only touched after the previous grid has completed.
+  pdl_launch_dependents();
+  if (warp != 0) pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------ weight producer (1-D bulk copies)
@@ -449,8 +454,17 @@ static cudaError_t launch_one(const CUtensorMap* maps, const TcConvParams& p, in
     configured = smem;
   }
   (void)n_blocks;
-  kern<<<grid_ctas, kTcThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid_ctas));
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
 }
 
 template <int N_T, int KC, int MS>

@@ -259,6 +259,38 @@ class Generator(nn.Module):
         kernel (the tail of reference hifiapi.py:47-51).  Returns a device int16 tensor [B,1,N]."""
         return self._run(x, _native.OUT_I16, float(max_wav_value))
 
+    @torch.no_grad()
+    def make_graphed(self, B: int, T: int, out_int16: bool = False, max_wav_value: float = 32768.0):
+        """Capture one forward for a fixed [B, 80, T] shape into a CUDA graph and return a callable
+        ``run(mel) -> wav``.  The reference has nothing comparable (eager, default
+        stream); this is for the small-T latency regime (BASELINE cfg-1), where the ~60 kernel
+        launches of a forward cost more than their execution.  ``run`` copies ``mel`` (any strides,
+        same device) into a static buffer, replays the graph and returns the static output tensor —
+        clone it if it must survive the next call."""
+        eng = self._get_engine()
+        dev = eng.device
+        static_in = torch.zeros((B, NUM_MELS, T), device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):  # warm-up outside capture: tensor maps, function attributes, workspace
+                    static_out = self._run(static_in, _native.OUT_I16 if out_int16 else _native.OUT_F32, max_wav_value)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self._run(static_in, _native.OUT_I16 if out_int16 else _native.OUT_F32, max_wav_value)
+
+        def run(mel: torch.Tensor) -> torch.Tensor:
+            if tuple(mel.shape) != (B, NUM_MELS, T):
+                raise RuntimeError(f"graphed generator expects input[{B}, {NUM_MELS}, {T}], got {list(mel.shape)}")
+            static_in.copy_(mel, non_blocking=True)
+            graph.replay()
+            return static_out
+
+        run.graph = graph  # keep the graph (and its private workspace) alive with the callable
+        return run
+
     @property
     def hop_length(self) -> int:
         n = 1
