@@ -28,6 +28,9 @@ cudaError_t launch_f32_to_operand(const float* x, long long n, float slope, int 
 int run_tcgen05_selftest(char* buf, size_t len);
 cudaError_t launch_conv_narrow(int c, NarrowConvParams p, cudaStream_t st);
 size_t conv_pair_smem_bytes(int c, int slab_rows, int t_rows, int t_bufs, int stages);
+size_t conv_tc2_smem_bytes(int n_t, int slab_rows, int nbuf, int stages, int epi_slot_bytes);
+cudaError_t launch_conv_tc2(int n_t, int ms, const CUtensorMap* maps, const TcConvParams& p, size_t smem, int grid,
+                            cudaStream_t st);
 cudaError_t launch_conv_pair_tc(int c, const CUtensorMap& m, const CUtensorMap& mr, const TcPairParams& p, size_t smem,
                                 int grid, cudaStream_t st);
 }  // namespace hg
@@ -162,6 +165,34 @@ static int make_tile_map(HgPlan* plan, const void* ptr, int L, int B, int c, int
   *out = m;
   return HG_OK;
 }
+// packed (pre-swizzled) bf16 weight image seen as a plain 2-D tensor [rows][64]: a box of `box_rows`
+// rows is one CTA's half of a weight tile in the CTA-pair kernel (no TMA swizzle: bytes land as packed)
+static int make_weight_map(HgPlan* plan, const void* ptr, long long rows, int box_rows, CUtensorMap* out) {
+  MapKey key(ptr, static_cast<int>(rows), 0, 64, -10, box_rows);
+  {
+    std::lock_guard<std::mutex> g(plan->mu);
+    auto it = plan->maps.find(key);
+    if (it != plan->maps.end()) { *out = it->second; return HG_OK; }
+  }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(HG_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {64, static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(HG_ECUDA, "cuTensorMapEncodeTiled (weights) failed (%d)", static_cast<int>(r));
+  {
+    std::lock_guard<std::mutex> g(plan->mu);
+    plan->maps[key] = m;
+  }
+  *out = m;
+  return HG_OK;
+}
+
 static int make_f32_tile_map(HgPlan* plan, const void* ptr, int L, int B, int c, CUtensorMap* out) {
   return make_tile_map(plan, ptr, L, B, c, 0, out);
 }
@@ -240,6 +271,7 @@ extern "C" int hg_plan_create(const HgConfig* cfg, int device, HgPlan** out) {
   p->ctas_per_sm = env_int("HG_TC_CTAS_PER_SM", 1);
   p->fuse_pairs = env_int("HG_FUSE_PAIRS", 1) != 0;
   p->epi_tma = env_int("HG_EPI_TMA", 1) != 0;
+  p->use_tc2 = env_int("HG_TC2", 1) != 0;
   const int uic = cfg->upsample_initial_channel;
   p->layers.push_back(make_conv("conv_pre", cfg->num_mels, uic, 7, 1));
   for (int i = 0; i < cfg->num_upsamples; ++i) {
@@ -502,6 +534,48 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
     if (tma_epi) {
       slot = (epi.res ? 2048 : 0) + (epi.out_x ? 2048 : 0) + (epi.out_a0 ? (split ? 2048 : 1024) : 0);
       slot = std::max(slot, 1024);
+    }
+    // CTA-pair kernel (conv_tc2.cu) for the wide same-length convs in bf16 mode
+    // — whenever the single-CTA kernel could not keep the layer's weights resident in shared memory
+    if (plan->use_tc2 && tma_epi && !split && l.n_blocks == 1 && l.kc == 64 && (l.n_tile == 128 || l.n_tile == 256) &&
+        !choose_tiling(plan, l, split, slot).resident) {
+      int min_off = l.tap_off[0], max_off = l.tap_off[0];
+      for (int j = 1; j < l.ntaps; ++j) { min_off = std::min(min_off, l.tap_off[j]); max_off = std::max(max_off, l.tap_off[j]); }
+      const int ms = l.n_tile == 256 ? 1 : 2;
+      const int need = ms * 128 + (max_off - min_off);
+      const int nboxes = (need + 255) / 256;
+      const int box_rows = (((need + nboxes - 1) / nboxes) + 7) / 8 * 8;
+      const int slab_rows = nboxes * box_rows;
+      const size_t kMaxSmem = 227 * 1024;
+      int nbuf = 2, stages = 12;
+      while (stages >= 3 && conv_tc2_smem_bytes(l.n_tile, slab_rows, nbuf, stages, slot) > kMaxSmem) --stages;
+      if (stages >= 3) {
+        if (conv_tc2_smem_bytes(l.n_tile, slab_rows, 3, stages, slot) <= kMaxSmem && stages >= 6) nbuf = 3;
+        TcConvParams p;
+        memset(&p, 0, sizeof(p));
+        p.B = B; p.rows = rows;
+        p.tiles_per_item = (rows + 2 * ms * 128 - 1) / (2 * ms * 128);
+        p.nc = l.nc; p.ntaps = l.ntaps;
+        for (int j = 0; j < l.ntaps; ++j) p.tap_row[j] = l.tap_off[j] - min_off;
+        p.min_off = min_off; p.slab_rows = slab_rows; p.box_rows = box_rows; p.nboxes = nboxes;
+        p.nbuf = nbuf; p.stages = stages; p.n_blocks = 1;
+        p.total_work = B * p.tiles_per_item;
+        p.epi = epi; p.epi_tma = 1; p.epi_slot_bytes = slot;
+        CUtensorMap maps[5];
+        int rc = make_operand_map(plan, in.a0, L_in, B, l.cin_pad, 64, box_rows, &maps[0]);
+        if (rc) return rc;
+        if ((rc = make_weight_map(plan, l.w_hi, static_cast<long long>(l.nc) * l.ntaps * l.n_tile, l.n_tile / 2, &maps[1]))) return rc;
+        maps[2] = maps[3] = maps[4] = maps[0];
+        if (epi.res) { p.has_res = 1; if ((rc = make_tile_map(plan, epi.res, L_in, B, l.cout, 1, &maps[2]))) return rc; }
+        if (epi.out_x) { p.has_x = 1; if ((rc = make_tile_map(plan, epi.out_x, L_in, B, l.cout, 1, &maps[3]))) return rc; }
+        if (epi.out_a0) { p.has_a = 1; if ((rc = make_tile_map(plan, epi.out_a0, L_in, B, l.cout, 2, &maps[4]))) return rc; }
+        const int pairs = std::min(p.total_work, plan->sm_count / 2);
+        const size_t smem = conv_tc2_smem_bytes(l.n_tile, slab_rows, nbuf, stages, slot);
+        cudaError_t e = launch_conv_tc2(l.n_tile, ms, maps, p, smem, 2 * pairs, st);
+        if (e != cudaSuccess) return fail(HG_ECUDA, "conv_tc2 launch (%s): %s", l.name.c_str(), cudaGetErrorString(e));
+        if (g_prof) prof_mark(static_cast<int>(&l - plan->layers.data()));
+        return HG_OK;
+      }
     }
     TcTiling t = choose_tiling(plan, l, split, slot);
     if (tma_epi && (t.stages < 3 && !t.resident)) {
@@ -944,6 +1018,7 @@ static int op_layer(int device, int precision, Layer& l, const float* x, int B, 
   plan.force_ffma = env_int("HG_FORCE_FFMA", 0) != 0;
   plan.ctas_per_sm = env_int("HG_TC_CTAS_PER_SM", 1);
   plan.epi_tma = env_int("HG_EPI_TMA", 1) != 0;
+  plan.use_tc2 = env_int("HG_TC2", 1) != 0;
   {
     cudaDeviceProp pr;
     if (cudaGetDeviceProperties(&pr, device) == cudaSuccess) plan.sm_count = pr.multiProcessorCount;

@@ -62,6 +62,7 @@ struct HgPlan {
   int ctas_per_sm = 1;  // persistent grid = min(work, SMs * ctas_per_sm)
   bool fuse_pairs = true;  // HG_FUSE_PAIRS=0: never use the fused ResBlock-pair kernel
   bool epi_tma = true;     // HG_EPI_TMA=0: always use the generic (LSU) epilogue in conv_tc
+  bool use_tc2 = true;     // HG_TC2=0: never use the CTA-pair (cta_group::2) kernel for the 256/128-channel convs
   bool force_ffma = false;  // HG_FORCE_FFMA=1: route every layer to the CUDA-core kernel
   std::mutex mu;
   std::map<hg::MapKey, CUtensorMap> maps;
