@@ -221,3 +221,35 @@ def test_multi_gpu_sharding_matches_single_gpu():
     for prec in ("fp32", "bf16"):
         assert res[prec]["utterance_sharding_bitwise_equal"]
         assert res[prec]["long_form_max_abs_vs_single_gpu"] <= 1e-6
+
+
+@pytest.mark.parametrize("env", [{"HG_TC2": "0"}, {"HG_FUSE_PAIRS": "0"}, {"HG_EPI_TMA": "0"},
+                                 {"HG_TC2": "0", "HG_FUSE_PAIRS": "0", "HG_EPI_TMA": "0"}, {"HG_FORCE_FFMA": "1"}])
+def test_alternative_kernel_paths_keep_parity(env):
+    """Every layer has more than one kernel path (CTA-pair / single-CTA tcgen05, fused / unfused
+    ResBlock pairs, TMA / generic epilogue, CUDA-core).  Each combination must meet the same
+    tolerances; the switches are read at plan creation, so each runs in its own process."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, json, torch, numpy as np\n"
+        f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})\n"
+        "from oracle import fixtures as fx\n"
+        "from oracle.common import max_abs, snr_db\n"
+        "from _util import golden, make_generator\n"
+        "g = golden('v1_seed1234'); out = {}\n"
+        "for prec in ('fp32', 'bf16'):\n"
+        "    m = make_generator(fx.V1, precision=prec).cuda()\n"
+        "    with torch.no_grad():\n"
+        "        y = m(torch.from_numpy(g['mel_b']).cuda()).cpu().numpy()\n"
+        "    out[prec] = [max_abs(y, g['y_b']), snr_db(g['y_b'], y)]\n"
+        "print(json.dumps(out))\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env={**os.environ, **env})
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert res["fp32"][0] <= FP32_TOL, res
+    assert res["bf16"][1] >= BF16_SNR_DB, res

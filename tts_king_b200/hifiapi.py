@@ -72,6 +72,11 @@ class HIFIapi:
         """
         self.model.eval()
         with torch.no_grad():
-            audio = self.model.generate_int16(mel_specs.to(self.compute_device), float(self.cfg.hifi.MAX_WAV_VALUE))
-            audio = audio.cpu().numpy()
-        return audio
+            mel_dev = mel_specs.to(self.compute_device, non_blocking=True)
+            audio = self.model.generate_int16(mel_dev, float(self.cfg.hifi.MAX_WAV_VALUE))
+            # device -> pinned host at full PCIe rate (a pageable .cpu() is staged and ~3x slower); the
+            # pinned block comes from torch's caching host allocator and is owned by the returned array
+            host = torch.empty(audio.shape, dtype=audio.dtype, pin_memory=True)
+            host.copy_(audio, non_blocking=True)
+            torch.cuda.current_stream(self.compute_device).synchronize()
+        return host.numpy()
