@@ -742,7 +742,27 @@ static int run_pair(HgPlan* plan, const Layer& l1, const Layer& l2, const PairTi
   epi.res = nullptr;  // the kernel adds the residual from its TMA-loaded tile
   p.epi = epi;
   const int grid = std::min(p.total_work, plan->sm_count);
+  static long long* dbg_buf = nullptr;
+  const char* dbg_layer = getenv("HG_TC_DEBUG_TIMING");  // layer name (the pair's c2) to instrument (bring-up only)
+  if (dbg_layer && l2.name == dbg_layer) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 256 * 16 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 256 * 16 * sizeof(long long), st);
+    p.dbg = dbg_buf;
+  }
   cudaError_t e = launch_conv_pair_tc(c, m, mr, p, t.smem, grid, st);
+  if (p.dbg && e == cudaSuccess) {
+    std::vector<long long> h(256 * 16);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), dbg_buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    double s[16] = {0};
+    for (int i = 0; i < grid; ++i)
+      for (int j = 0; j < 16; ++j) s[j] += static_cast<double>(h[i * 16 + j]) / grid;
+    fprintf(stderr,
+            "[hg dbg] %s pair k=%d d=%d grid=%d tiles/cta=%.1f resident=%d stages=%d t_bufs=%d | MMA warp: total=%.0f wait weights=%.0f d1_empty=%.0f "
+            "slab=%.0f t_full=%.0f d2_empty=%.0f | epi warp 0: total=%.0f wait d1_full=%.0f t_empty=%.0f d2_full=%.0f res=%.0f; busy E1=%.0f E2=%.0f\n",
+            l2.name.c_str(), p.k, p.d1, grid, s[6], p.w_resident, p.stages, p.t_bufs, s[0], s[1], s[2], s[3], s[4], s[5], s[8], s[9], s[10],
+            s[11], s[12], s[13], s[14]);
+  }
   if (e != cudaSuccess) return fail(HG_ECUDA, "conv_pair_tc launch (%s): %s", l2.name.c_str(), cudaGetErrorString(e));
   if (g_prof) prof_mark(static_cast<int>(&l2 - plan->layers.data()));
   return HG_OK;

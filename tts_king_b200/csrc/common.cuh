@@ -367,6 +367,7 @@ struct TcPairParams {
   const uint8_t* w2;   //                                         (conv 2)
   const float* bias1;  // [C]
   float slope;         // leaky_relu slope applied to xt (0.1)
+  long long* dbg;      // optional [grid][16] cycle counters (HG_TC_DEBUG_TIMING): wait breakdown
   EpiParams epi;       // epilogue of c2
 };
 

@@ -152,13 +152,20 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
     const uint32_t wst_lo = (smem_u32(wst) & 0x3FFFFu) >> 4;
     int stage = 0; uint32_t wphase = 0;
     bool w_seen = false;  // resident mode: every stage has been waited for once
+    // bring-up instrumentation (HG_TC_DEBUG_TIMING): cycles spent in each wait, kept in global memory
+    long long* dbg = p.dbg ? p.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
+    const long long c_t0 = dbg ? clock64() : 0;
+    auto timed_wait = [&](uint64_t* bar, uint32_t ph, int slot) {
+      if (dbg) { const long long t0 = clock64(); mbar_wait(bar, ph); if (lane == 0) dbg[slot] += clock64() - t0; }
+      else mbar_wait(bar, ph);
+    };
 
     // one GEMM: k taps, A = base + tap*row_step rows, accumulate into `acc`
     auto gemm = [&](uint32_t a_base_lo, uint32_t tap_step_lo, uint32_t acc, int conv) {
       for (int t = 0; t < p.k; ++t) {
         const int st = p.w_resident ? conv * p.k + t : stage;
         if (!p.w_resident || !w_seen) {
-          mbar_wait(&w_full[st], p.w_resident ? 0u : wphase);
+          timed_wait(&w_full[st], p.w_resident ? 0u : wphase, 1);
           tc_fence_after();
         }
         const uint32_t b_lo = wst_lo + static_cast<uint32_t>(st) * (STAGE_BYTES >> 4);
@@ -180,8 +187,8 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
     auto g1 = [&](int i) {
       const int buf = i & 1;
       const uint32_t ph = (i >> 1) & 1;
-      mbar_wait(&d1_empty[buf], ph ^ 1);
-      mbar_wait(&slab_full[buf], ph);
+      timed_wait(&d1_empty[buf], ph ^ 1, 2);
+      timed_wait(&slab_full[buf], ph, 3);
       tc_fence_after();
       gemm(slab_lo + static_cast<uint32_t>(buf) * (static_cast<uint32_t>(slab_bytes) >> 4),
            (static_cast<uint32_t>(p.d1) * ROWB) >> 4, tmem_u + buf * ACC_COLS, 0);
@@ -193,8 +200,8 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
       const uint32_t ph = (i >> 1) & 1;
       const int tbi = p.t_bufs == 2 ? buf : 0;
       const uint32_t tph = p.t_bufs == 2 ? ph : static_cast<uint32_t>(i & 1);
-      mbar_wait(&t_full[tbi], tph);
-      mbar_wait(&d2_empty[buf], ph ^ 1);
+      timed_wait(&t_full[tbi], tph, 4);
+      timed_wait(&d2_empty[buf], ph ^ 1, 5);
       tc_fence_after();
       gemm(t_lo + static_cast<uint32_t>(tbi) * (static_cast<uint32_t>(t_bytes) >> 4), ROWB >> 4,
            tmem_u + (2 + buf) * ACC_COLS, 1);
@@ -207,6 +214,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
       g2(i);
       w_seen = true;
     }
+    if (dbg && lane == 0) { dbg[0] = clock64() - c_t0; dbg[6] = n_my; }
   } else {
     // ------------------------------------------------ epilogue warps (all 16 do E1 then E2)
     const int e = warp - 3;
@@ -219,6 +227,13 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
     constexpr int E2_CH = N_T / 32;
     const int ms2 = sub / E2_CH, c02 = (sub - ms2 * E2_CH) * 32;
     const int n2 = c02 + c4 * 4;
+    // bring-up instrumentation (HG_TC_DEBUG_TIMING): cycles spent in each wait, kept in global memory
+    long long* dbg = (p.dbg && e == 0) ? p.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
+    const long long c_t0 = dbg ? clock64() : 0;
+    auto timed_wait = [&](uint64_t* bar, uint32_t ph, int slot) {
+      if (dbg) { const long long t0 = clock64(); mbar_wait(bar, ph); if (lane == 0) dbg[slot] += clock64() - t0; }
+      else mbar_wait(bar, ph);
+    };
 
     // E1: D1 -> (+b1, leaky_relu, bf16) -> xt tile in UMMA layout; two (sub-tile, 16-column) items
     auto e1 = [&](int i) {
@@ -229,9 +244,10 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
       const uint32_t ph = (i >> 1) & 1;
       const int tbi = p.t_bufs == 2 ? buf : 0;
       const uint32_t tph = p.t_bufs == 2 ? ph : static_cast<uint32_t>(i & 1);
-      mbar_wait(&d1_full[buf], ph);
-      mbar_wait(&t_empty[tbi], tph ^ 1);  // the G2 that last read this xt buffer has retired
+      timed_wait(&d1_full[buf], ph, 9);
+      timed_wait(&t_empty[tbi], tph ^ 1, 10);  // the G2 that last read this xt buffer has retired
       tc_fence_after();
+      const long long c_s = dbg ? clock64() : 0;
       uint8_t* tb = tbuf + tbi * t_bytes;
       const uint32_t tmem_acc = tmem_base + buf * ACC_COLS + lane_base;
       constexpr int ITEMS = MS * (N_T / 16);
@@ -269,6 +285,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
       fence_proxy_async();  // generic-proxy writes of xt -> visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_full[tbi]);
+      if (dbg && lane == 0) dbg[13] += clock64() - c_s;
     };
 
     // E2: D2 + residual -> smem transpose -> fused epilogue of c2.  The fp32 residual tile of this
@@ -290,8 +307,9 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
       int b, m0;
       coords(i, b, m0);
       const int buf = i & 1;
-      mbar_wait(&d2_full[buf], (i >> 1) & 1);
+      timed_wait(&d2_full[buf], (i >> 1) & 1, 11);
       tc_fence_after();
+      const long long c_s = dbg ? clock64() : 0;
       {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (2 + buf) * ACC_COLS + lane_base + ms2 * N_T + c02, r);
@@ -299,7 +317,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&d2_empty[buf]);
-        mbar_wait(&res_bar[e], i & 1);
+        timed_wait(&res_bar[e], i & 1, 12);
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
           float4* sp = reinterpret_cast<float4*>(stg + lane * 32 + ((k4 ^ (lane & 7)) << 2));
@@ -322,6 +340,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
       if (lane == 0 && i + 1 < n_my) prefetch_res(i + 1);
       epilogue_rows<8, false>(p.epi, b, static_cast<long long>(m0) + ms2 * 128 + quarter * 32 + rsub, 4, n2, v,
                        static_cast<long long>(m0) + p.r_out);
+      if (dbg && lane == 0) dbg[14] += clock64() - c_s;
     };
     if (n_my > 0) {
       if (lane == 0) prefetch_res(0);
@@ -331,6 +350,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
       if (i + 1 < n_my) e1(i + 1);
       e2(i);
     }
+    if (dbg && lane == 0) dbg[8] = clock64() - c_t0;
   }
 
   tc_fence_before();
