@@ -121,6 +121,27 @@ HG_API int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC, in
                void* out, int out_dtype, float out_scale, int precision, void* workspace,
                size_t workspace_bytes, void* stream);
 
+/*
+ * Mel frames of right context a sample needs (13 for V1): the generator's
+ * receptive reach, rounded up to frames.  What hg_forward_ragged adds to every item's length.
+ */
+HG_API int hg_halo_frames(const HgPlan* plan, int* frames);
+
+/*
+ * hg_forward for a padded batch whose items have their own lengths — the vocoder call of
+ * synth_samples, fs_two/utils/tools.py:257-268 + fs_two/utils/model.py:85-100, where the reference
+ * runs the generator over the padding and trims the waveforms to `lengths` afterwards.
+ *   frames   HOST array [B]: mel frames item b keeps, 1 <= frames[b] <= T.  B <= 64.
+ * Every layer computes item b's rows only up to (frames[b] + hg_halo_frames) frames (the last
+ * one up to frames[b]); `out` is written for b on [0, frames[b] * hop), rounded up to the last
+ * kernel's 256-sample tile, and left untouched beyond.  Inside [0, frames[b] * hop) the result is
+ * bit-identical to hg_forward on the same padded input, whatever the padding and the scratch hold;
+ * samples of that last tile past frames[b] * hop are unspecified (none when hop is a multiple of 256).
+ */
+HG_API int hg_forward_ragged(HgPlan* plan, const float* mel, int64_t sB, int64_t sC, int64_t sT, int B, int T,
+                      const int32_t* frames, void* out, int out_dtype, float out_scale, int precision,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* Frees device weights and host state. */
 HG_API int hg_plan_destroy(HgPlan* plan);
 

@@ -160,6 +160,84 @@ def test_batch_items_are_independent(prec):
     assert torch.equal(yb, ys)
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_ragged_batch_is_bit_identical_inside_valid_ranges(prec):
+    """N2: length buckets skip the padding the reference computes (fs_two/utils/tools.py:257-268) and
+    change nothing on the samples vocoder_infer keeps."""
+    from tts_king_b200 import ragged
+
+    m = make_generator(fx.V1, precision=prec).cuda()
+    T = 120
+    mel = fx.synthetic_mel(6, T, seed=31).cuda()  # padding frames are not zero: they must not matter
+    keep = [T * 256, 37 * 256 + 5, 38 * 256, 1, 90 * 256 - 1, 64 * 256]
+    assert m._get_engine().halo_frames() == parallel.halo_frames(m.h) == 13
+    with torch.no_grad():
+        full = m(mel)
+        full16 = m.generate_int16(mel)
+        for mode in ("kernel", "buckets"):
+            parts = ragged.ragged_generate(m, mel, keep, out_int16=False, launch_cost=8, mode=mode)
+            parts16 = ragged.ragged_generate(m, mel, keep, out_int16=True, launch_cost=8, mode=mode)
+            for i, n in enumerate(keep):
+                assert torch.equal(parts[i], full[i, 0, :n]), (mode, i)
+                assert torch.equal(parts16[i], full16[i, 0, :n]), (mode, i)
+        # the kernel path on poisoned scratch: whatever the skipped rows hold must not leak into kept samples
+        frames = [-(-n // 256) for n in keep]
+        m(torch.full_like(mel, float("nan")))  # leaves NaN in every workspace buffer
+        y = m.forward_ragged(mel, frames)
+        for i, n in enumerate(keep):
+            assert torch.equal(y[i, 0, :n], full[i, 0, :n]), i
+            assert (y[i, 0, frames[i] * 256:] == 0).all(), i  # the skipped tail reads as silence, not scratch
+    with pytest.raises(ValueError):
+        m.forward_ragged(mel, frames[:-1])
+    with pytest.raises(RuntimeError):
+        m.forward_ragged(mel, [0] + frames[1:])  # frames must be in [1, T]
+
+
+@pytest.mark.parametrize("name,cfg", [("v2_narrow", fx.V2_NARROW), ("v3_rb2", fx.V3_RB2)])
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "fp32_ffma"])
+def test_ragged_other_configs_and_paths(name, cfg, prec):
+    """The compacted tile space goes through every kernel family (narrow, FFMA, non-fused tcgen05)."""
+    m = make_generator(cfg, precision=prec).cuda()
+    hop = m.hop_length
+    mel = fx.synthetic_mel(4, 70, seed=17).cuda()
+    frames = [70, 9, 33, 1]
+    with torch.no_grad():
+        full = m(mel)
+        y = m.forward_ragged(mel, frames)
+    for i, f in enumerate(frames):
+        assert torch.equal(y[i, 0, :f * hop], full[i, 0, :f * hop]), i
+
+
+def test_vocoder_infer_drop_in():
+    """N1/N2: fs_two/utils/model.py:85-100 — list of int16 arrays, trimmed to `lengths`."""
+    from tts_king_b200.fs_two.utils.model import vocoder_infer
+
+    mc = {"vocoder": {"model": "HiFi-GAN"}}
+    pc = {"preprocessing": {"audio": {"max_wav_value": 32768.0}}}
+    # against the reference's own (forward * 32768).astype(int16) (tools/make_golden.py)
+    g = golden("tiny_rb1")
+    m = make_generator(fx.TINY_RB1, seed=6, fold=True)
+    m.load_state_dict(stored_state(g, "alive."))
+    m.cuda()
+    ref16 = g["y_alive_int16"]
+    wavs = vocoder_infer(torch.from_numpy(g["mel"]), m, mc, pc)
+    assert isinstance(wavs, list) and len(wavs) == ref16.shape[0]
+    for i, w in enumerate(wavs):
+        assert w.dtype == np.int16 and w.shape == ref16[i, 0].shape
+        assert np.abs(w.astype(np.int32) - ref16[i, 0].astype(np.int32)).max() <= 4  # 1e-4 * 32768 = 3.3 LSB
+    # with lengths: same samples, padding not computed
+    m = make_generator(fx.V1).cuda()
+    mel = fx.synthetic_mel(5, 100, seed=41)
+    wavs = vocoder_infer(mel, m, mc, pc)
+    lengths = torch.tensor([100 * 256, 31 * 256 + 9, 1, 70 * 256, 30 * 256])
+    trimmed = vocoder_infer(mel, m, mc, pc, lengths=lengths)
+    assert len(trimmed) == 5
+    for i, w in enumerate(trimmed):
+        n = int(lengths[i])
+        assert w.dtype == np.int16 and w.shape == (n,)
+        assert np.array_equal(w, wavs[i][:n])  # bit-identical to the padded run
+
+
 def test_full_size_cross_check_against_ffma():
     """BASELINE cfg-2 scale (16 x 800 frames): the tensor-core fp32 path against the exact-fp32
     CUDA-core path on the device (the CPU oracle would take minutes), plus bf16 SNR."""

@@ -132,6 +132,72 @@ def test_chunked_forward_equals_full_forward():
     assert max_abs(y_bad.numpy(), full.numpy()) > 1e-9
 
 
+# ------------------------------------------------------------------ ragged batches (N2)
+def test_length_buckets_partition_and_cost():
+    from tts_king_b200 import ragged
+
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 7, 16, 33):
+        frames = [int(v) for v in rng.integers(1, 900, size=n)]
+        t_max = max(frames)
+        buckets = ragged.plan_length_buckets(frames, 13, t_max)
+        assert sorted(i for b in buckets for i in b) == list(range(n))  # a partition
+        assert buckets == ragged.plan_length_buckets(frames, 13, t_max)  # deterministic
+        cost = sum(len(b) * ragged.bucket_extent(frames, b, 13, t_max) + 400 for b in buckets)
+        assert cost <= n * t_max + 400  # never worse than the padded batch
+        for b in buckets:  # contiguous in sorted order: no bucket's range straddles another's
+            lo, hi = min(frames[i] for i in b), max(frames[i] for i in b)
+            assert all(not (lo < frames[j] < hi) for c in buckets if c is not b for j in c)
+    assert ragged.plan_length_buckets([800] * 16, 13, 800) == [list(range(16))]  # nothing to skip
+    assert ragged.plan_length_buckets([], 13, 800) == []
+    assert len(ragged.plan_length_buckets([100, 800] * 4, 13, 800, max_buckets=1)) == 1
+    assert len(ragged.plan_length_buckets([100, 800] * 4, 13, 800)) == 2
+    with pytest.raises(ValueError):
+        ragged.plan_length_buckets([3, 0], 13, 800)
+
+
+class _OracleGenerator:
+    """The CPU oracle behind the two attributes and the call ragged_generate uses."""
+
+    def __init__(self, cfg, sd):
+        self.cfg, self.sd, self.h = cfg, sd, fx.make_h(cfg)
+        self.hop_length = parallel.hop_length(self.h)
+        self.calls = []
+
+    def __call__(self, mel):
+        self.calls.append(tuple(mel.shape))
+        return torch_oracle.forward(self.cfg, self.sd, mel)
+
+
+def test_ragged_generate_equals_padded_forward_inside_valid_ranges():
+    """N2: length buckets + 13-frame tail == the padded forward on every kept sample."""
+    from tts_king_b200 import ragged
+
+    cfg = fx.TINY_RB1
+    sd = {k: v.double() for k, v in stored_state(golden("tiny_rb1"), "alive.").items()}
+    gen = _OracleGenerator(cfg, sd)
+    T = 96
+    mel = fx.synthetic_mel(5, T, seed=11).double()  # padding frames deliberately NOT zero
+    keep = [96 * 256, 20 * 256 + 17, 21 * 256, 1, 60 * 256 - 3]
+    full = gen(mel)
+    gen.calls.clear()
+    parts = ragged.ragged_generate(gen, mel, keep, out_int16=False, launch_cost=8)
+    assert len(gen.calls) >= 2 and sum(b * t for b, _, t in gen.calls) < 5 * T  # padding was skipped
+    for i, n in enumerate(keep):
+        assert parts[i].shape == (n,)
+        assert max_abs(parts[i].numpy(), full[i, 0, :n].numpy()) <= 1e-13
+    with pytest.raises(ValueError):
+        ragged.ragged_generate(gen, mel, keep[:-1], out_int16=False)
+
+
+def test_vocoder_infer_rejects_other_vocoders():
+    from tts_king_b200.fs_two.utils.model import vocoder_infer
+
+    with pytest.raises(NotImplementedError):
+        vocoder_infer(torch.zeros(1, 80, 4), None, {"vocoder": {"model": "MelGAN"}},
+                      {"preprocessing": {"audio": {"max_wav_value": 32768.0}}})
+
+
 # ------------------------------------------------------------------ world_size-2 gloo
 def _free_port():
     s = socket.socket()

@@ -18,15 +18,16 @@ namespace hg {
 size_t conv_tc_smem_bytes(int n_t, int kc, bool split, int slab_rows, int nbuf, int stages, int epi_slot_bytes);
 cudaError_t launch_conv_tc(int n_t, int kc, int ms, bool split, const CUtensorMap* maps, const TcConvParams& p,
                            int n_blocks, size_t smem, int grid_ctas, cudaStream_t st);
-cudaError_t launch_conv_ffma(const FfmaConvParams& p, cudaStream_t st);
+cudaError_t launch_conv_ffma(FfmaConvParams p, cudaStream_t st, const RaggedItems* items = nullptr);
 cudaError_t launch_conv_post(const float* x, int B, int L, int C, const float* w_tapmajor, float bias, float* out_f32,
-                             int16_t* out_i16, float out_scale, cudaStream_t st, const float* w_host_tapmajor);
+                             int16_t* out_i16, float out_scale, cudaStream_t st, const float* w_host_tapmajor,
+                             const RaggedItems* items = nullptr);
 cudaError_t launch_mel_to_operand(const float* mel, long long sB, long long sC, long long sT, int B, int C, int T,
                                   int c_pad, int a_fmt, void* a0, void* a1, cudaStream_t st);
 cudaError_t launch_f32_to_operand(const float* x, long long n, float slope, int a_fmt, void* a0, void* a1,
                                   cudaStream_t st);
 int run_tcgen05_selftest(char* buf, size_t len);
-cudaError_t launch_conv_narrow(int c, NarrowConvParams p, cudaStream_t st);
+cudaError_t launch_conv_narrow(int c, NarrowConvParams p, cudaStream_t st, const RaggedItems* items = nullptr);
 size_t conv_pair_smem_bytes(int c, int slab_rows, int t_rows, int t_bufs, int stages);
 size_t conv_tc2_smem_bytes(int n_t, int slab_rows, int nbuf, int stages, int epi_slot_bytes);
 cudaError_t launch_conv_tc2(int n_t, int ms, const CUtensorMap* maps, const TcConvParams& p, size_t smem, int grid,
@@ -452,6 +453,55 @@ static void prof_mark(int layer_index) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// ragged batches (hg_forward_ragged): item b needs (frames[b] + halo) mel frames' worth of rows at
+// every layer — the generator's receptive reach, SURVEY.md App. E — and nothing beyond
+struct RaggedCtx {
+  const int32_t* frames;  // host, [B]
+  int halo;               // mel frames
+  int T;
+};
+static thread_local const RaggedCtx* g_rag = nullptr;
+
+// valid GEMM rows per item for a launch whose input has L_in rows per item (rows = L_in + extra)
+static const RaggedItems* ragged_items(RaggedItems* store, int B, int L_in, int extra, bool with_halo = true) {
+  if (!g_rag) return nullptr;
+  const long long per_frame = L_in / g_rag->T;  // exact: every stage length is T * prod(rates so far)
+  store->n = B;
+  for (int b = 0; b < B; ++b) {
+    const long long v = (static_cast<long long>(g_rag->frames[b]) + (with_halo ? g_rag->halo : 0)) * per_frame + extra;
+    store->valid_rows[b] = static_cast<int>(std::min<long long>(v, static_cast<long long>(L_in) + extra));
+  }
+  return store;
+}
+
+// receptive reach of one output sample beyond the frames that own it, in samples per side
+// (3 258 for V1; same walk as tts_king_b200/parallel.py::receptive_reach_samples)
+static long long reach_samples(const HgConfig& c) {
+  long long reach = 3;  // conv_pre k7
+  const int nd = c.resblock_type == 1 ? 3 : 2;
+  for (int i = 0; i < c.num_upsamples; ++i) {
+    const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i];
+    reach = reach * u + (k - u + 1) / 2;
+    long long blk = 0;
+    for (int j = 0; j < c.num_kernels; ++j) {
+      const int half = (c.resblock_kernel_sizes[j] - 1) / 2;
+      long long r = 0;
+      for (int d = 0; d < nd; ++d) r += static_cast<long long>(half) * c.resblock_dilation_sizes[j][d];
+      if (c.resblock_type == 1) r += static_cast<long long>(nd) * half;
+      blk = std::max(blk, r);
+    }
+    reach += blk;
+  }
+  return reach + 3;  // conv_post k7
+}
+
+static int halo_frames_of(const HgConfig& c) {
+  long long hop = 1;
+  for (int i = 0; i < c.num_upsamples; ++i) hop *= c.upsample_rates[i];
+  return static_cast<int>((reach_samples(c) + hop - 1) / hop);
+}
+
+// ------------------------------------------------------------------------------------------------
 // launching one GEMM-shaped layer
 struct OperandBuf {
   void* a0 = nullptr;
@@ -525,6 +575,8 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
   epi.out_extent = L_out * l.cout;
   epi.out_row_stride = l.n_total;
   epi.out_offset = l.kind == L_CONVT ? -static_cast<long long>(l.pad) * l.cout : 0;
+  RaggedItems rag_store;
+  const RaggedItems* rag = ragged_items(&rag_store, B, L_in, rows - L_in);
   if (use_tc(plan, l, precision)) {
     const bool split = precision == HG_PREC_FP32;
     // TMA epilogue for same-length convs without MRF accumulate (68 of the 78 layers of V1); its
@@ -559,7 +611,7 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
         for (int j = 0; j < l.ntaps; ++j) p.tap_row[j] = l.tap_off[j] - min_off;
         p.min_off = min_off; p.slab_rows = slab_rows; p.box_rows = box_rows; p.nboxes = nboxes;
         p.nbuf = nbuf; p.stages = stages; p.n_blocks = 1;
-        p.total_work = B * p.tiles_per_item;
+        p.total_work = ragged_fill(&p.rag, rag, B, rows, 2 * ms * 128);
         p.epi = epi; p.epi_tma = 1; p.epi_slot_bytes = slot;
         CUtensorMap maps[5];
         int rc = make_operand_map(plan, in.a0, L_in, B, l.cin_pad, 64, box_rows, &maps[0]);
@@ -595,7 +647,7 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
       p.nbuf = t.nbuf; p.stages = t.stages; p.desc_mode = plan->desc_mode;
       p.w_resident = t.resident ? 1 : 0;
       p.n_blocks = l.n_blocks;
-      p.total_work = B * p.tiles_per_item * l.n_blocks;
+      p.total_work = ragged_fill(&p.rag, rag, B, rows, t.ms * 128) * l.n_blocks;
       p.w_hi = l.w_hi; p.w_lo = l.w_lo; p.epi = epi;
       CUtensorMap maps[6];
       int rc = make_operand_map(plan, in.a0, L_in, B, l.cin_pad, l.kc, t.box_rows, &maps[0]);
@@ -645,7 +697,7 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
     np.B = B; np.L = L_in; np.k = l.k; np.dil = l.dil;
     np.a0 = in.a0; np.a1 = in.a1; np.a_fmt = a_fmt_of(precision);
     np.w = l.w_ffma; np.epi = epi;
-    cudaError_t e = launch_conv_narrow(l.cin, np, st);
+    cudaError_t e = launch_conv_narrow(l.cin, np, st, rag);
     if (e != cudaSuccess) return fail(HG_ECUDA, "conv_narrow launch (%s): %s", l.name.c_str(), cudaGetErrorString(e));
     if (g_prof) prof_mark(static_cast<int>(&l - plan->layers.data()));
     return HG_OK;
@@ -657,7 +709,7 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
   for (int j = 0; j < l.ntaps; ++j) f.tap_off[j] = l.tap_off[j];
   f.a0 = in.a0; f.a1 = in.a1; f.a_fmt = a_fmt_of(precision);
   f.w = l.w_ffma; f.epi = epi;
-  cudaError_t e = launch_conv_ffma(f, st);
+  cudaError_t e = launch_conv_ffma(f, st, rag);
   if (e != cudaSuccess) return fail(HG_ECUDA, "conv_ffma launch (%s): %s", l.name.c_str(), cudaGetErrorString(e));
   if (g_prof) prof_mark(static_cast<int>(&l - plan->layers.data()));
   return HG_OK;
@@ -728,7 +780,8 @@ static int run_pair(HgPlan* plan, const Layer& l1, const Layer& l2, const PairTi
   memset(&p, 0, sizeof(p));
   p.B = B; p.L = L; p.r_out = t.r_out;
   p.tiles_per_item = (L + t.r_out - 1) / t.r_out;
-  p.total_work = B * p.tiles_per_item;
+  RaggedItems rag_store;
+  p.total_work = ragged_fill(&p.rag, ragged_items(&rag_store, B, L, 0), B, L, t.r_out);
   p.k = l1.k; p.d1 = l1.dil;
   p.slab_rows = t.slab_rows; p.box_rows = t.box_rows; p.nboxes = t.nboxes; p.t_rows = t.t_rows; p.t_bufs = t.t_bufs;
   p.stages = t.stages; p.w_resident = t.resident ? 1 : 0;
@@ -958,13 +1011,36 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
   }
   // x = tanh(conv_post(leaky_relu(x)))  :197-199  (+ optional int16 tail, hifiapi.py:50-51)
   const Layer& post = plan->layers.back();
+  RaggedItems rag_store;
   e = launch_conv_post(x_final, B, L, post.cin, post.w_post, post.bias_post,
                        out_dtype == HG_OUT_F32 ? static_cast<float*>(out) : nullptr,
                        out_dtype == HG_OUT_I16 ? static_cast<int16_t*>(out) : nullptr, out_scale, st,
-                       post.w_post_host.empty() ? nullptr : post.w_post_host.data());
+                       post.w_post_host.empty() ? nullptr : post.w_post_host.data(),
+                       ragged_items(&rag_store, B, L, 0, /*with_halo=*/false));  // the last layer feeds nobody
   if (e != cudaSuccess) return fail(HG_ECUDA, "conv_post: %s", cudaGetErrorString(e));
   prof_mark(static_cast<int>(plan->layers.size()) - 1);
   return HG_OK;
+}
+
+extern "C" int hg_halo_frames(const HgPlan* plan, int* frames) {
+  if (!plan || !frames) return fail(HG_EINVAL, "null argument");
+  *frames = halo_frames_of(plan->cfg);
+  return HG_OK;
+}
+
+extern "C" int hg_forward_ragged(HgPlan* plan, const float* mel, int64_t sB, int64_t sC, int64_t sT, int B, int T,
+                                 const int32_t* frames, void* out, int out_dtype, float out_scale, int precision,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (!plan) return fail(HG_EINVAL, "null plan");
+  if (!frames) return fail(HG_EINVAL, "null frames");
+  if (B > kMaxRaggedItems) return fail(HG_EINVAL, "ragged batches hold at most %d items, got %d", kMaxRaggedItems, B);
+  for (int b = 0; b < B; ++b)
+    if (frames[b] < 1 || frames[b] > T) return fail(HG_EINVAL, "frames[%d] = %d outside [1, T = %d]", b, frames[b], T);
+  RaggedCtx ctx{frames, halo_frames_of(plan->cfg), T};
+  g_rag = &ctx;
+  const int rc = hg_forward(plan, mel, sB, sC, sT, B, T, out, out_dtype, out_scale, precision, workspace, workspace_bytes, stream);
+  g_rag = nullptr;
+  return rc;
 }
 
 extern "C" int hg_layer_count(const HgPlan* plan, int* count) {

@@ -17,6 +17,50 @@ namespace hg {
 
 constexpr int kMaxTaps = 16;
 
+// Ragged batches: item b only needs its first valid_rows[b] GEMM rows, so the tile
+// index space is compacted — tile t belongs to the item b with prefix[b] <= t < prefix[b+1] and is
+// that item's (t - prefix[b])-th tile.  The table travels in the kernel parameters (constant bank),
+// hence the bound on the batch size; n == 0 means a dense batch (every item has tiles_per_item tiles).
+constexpr int kMaxRaggedItems = 64;
+struct RaggedPrefix {
+  int n;
+  int prefix[kMaxRaggedItems + 1];
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ void decode_tile(const RaggedPrefix& r, int tiles_per_item, int t, int& b, int& tile) {
+  if (r.n == 0) {
+    b = t / tiles_per_item;
+    tile = t - b * tiles_per_item;
+    return;
+  }
+  int lo = 0, hi = r.n;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (r.prefix[mid] <= t) lo = mid; else hi = mid;
+  }
+  b = lo;
+  tile = t - r.prefix[lo];
+}
+#endif
+// host side: valid GEMM rows per item of one launch (n == 0: dense) -> prefix table; returns the tile count
+struct RaggedItems {
+  int n;
+  int valid_rows[kMaxRaggedItems];
+};
+inline int ragged_fill(RaggedPrefix* r, const RaggedItems* items, int B, int rows, int tile_rows) {
+  const int dense = (rows + tile_rows - 1) / tile_rows;
+  r->n = 0;
+  if (!items || items->n == 0) return B * dense;
+  r->n = B;
+  r->prefix[0] = 0;
+  for (int b = 0; b < B; ++b) {
+    int v = items->valid_rows[b] < rows ? items->valid_rows[b] : rows;
+    if (v < 1) v = 1;
+    r->prefix[b + 1] = r->prefix[b] + (v + tile_rows - 1) / tile_rows;
+  }
+  return r->prefix[B];
+}
+
 enum OperandFmt : int { A_BF16 = 0, A_BF16_SPLIT = 1, A_F32 = 2 };
 
 // Epilogue shared by every GEMM-shaped layer.  A GEMM element (item b, row q, column n) lands at
@@ -342,6 +386,7 @@ struct TcConvParams {
   int epi_slot_bytes;         // shared memory per epilogue warp (TMA: res | x | a_hi | a_lo tiles; generic: 2 KB)
   int desc_mode;  // how a tap's row shift enters the UMMA descriptor (see conv_tc.cu)
   long long* dbg;       // optional [grid][8] cycle counters (HG_TC_DEBUG_TIMING): MMA-warp wait breakdown
+  RaggedPrefix rag;     // ragged batch: compacted tile index space (n == 0: dense)
   const uint8_t* w_hi;  // packed swizzled weight tiles [n_blk][chunk][tap][N_T rows][KC]
   const uint8_t* w_lo;
   EpiParams epi;
@@ -368,6 +413,7 @@ struct TcPairParams {
   const float* bias1;  // [C]
   float slope;         // leaky_relu slope applied to xt (0.1)
   long long* dbg;      // optional [grid][16] cycle counters (HG_TC_DEBUG_TIMING): wait breakdown
+  RaggedPrefix rag;    // ragged batch: compacted tile index space (n == 0: dense)
   EpiParams epi;       // epilogue of c2
 };
 
@@ -381,6 +427,7 @@ struct FfmaConvParams {
   const void* a1;
   int a_fmt;
   const float* w;  // [tap][cin][n_total]
+  RaggedPrefix rag;
   EpiParams epi;
 };
 
@@ -391,6 +438,7 @@ struct NarrowConvParams {
   const void* a1;
   int a_fmt;
   const float* w;   // [k][C_in][C_out]  (the CUDA-core weight layout of plan.h)
+  RaggedPrefix rag;
   EpiParams epi;
 };
 

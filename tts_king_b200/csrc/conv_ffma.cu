@@ -21,8 +21,9 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(const FfmaConvParams p, 
   const int slab_rows = FT_M + span;
   float* slab = fsm;                             // [slab_rows][FT_K + 1]
   float* wsm = fsm + ((slab_rows * (FT_K + 1) + 3) & ~3);  // [FT_K][FT_N], 16B aligned
-  const int b = blockIdx.x / tiles_per_item;
-  const int m0 = (blockIdx.x - b * tiles_per_item) * FT_M;
+  int b, tile;
+  decode_tile(p.rag, tiles_per_item, static_cast<int>(blockIdx.x), b, tile);
+  const int m0 = tile * FT_M;
   const int n0 = blockIdx.y * FT_N;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float acc[4][4];
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(const FfmaConvParams p, 
   }
 }
 
-cudaError_t launch_conv_ffma(const FfmaConvParams& p, cudaStream_t st) {
+cudaError_t launch_conv_ffma(FfmaConvParams p, cudaStream_t st, const RaggedItems* items) {
   int min_off = p.tap_off[0], max_off = p.tap_off[0];
   for (int t = 1; t < p.ntaps; ++t) {
     min_off = p.tap_off[t] < min_off ? p.tap_off[t] : min_off;
@@ -97,7 +98,8 @@ cudaError_t launch_conv_ffma(const FfmaConvParams& p, cudaStream_t st) {
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return e;
   }
-  dim3 grid(static_cast<unsigned>(p.B * tiles), static_cast<unsigned>((p.n_total + FT_N - 1) / FT_N));
+  const int total = ragged_fill(&p.rag, items, p.B, p.rows, FT_M);
+  dim3 grid(static_cast<unsigned>(total), static_cast<unsigned>((p.n_total + FT_N - 1) / FT_N));
   conv_ffma_kernel<<<grid, 256, smem, st>>>(p, tiles, min_off, span);
   return cudaGetLastError();
 }

@@ -26,8 +26,9 @@ __global__ void __launch_bounds__(kNarrowThreads) conv_narrow_kernel(const Narro
   const int slab_rows = kNarrowRows + span;
   float* slab = nsm;                         // [slab_rows][PITCH]
   float* ws = nsm + slab_rows * PITCH;       // [k][C][C]
-  const int b = blockIdx.x / p.tiles_per_item;
-  const int t0 = (blockIdx.x - b * p.tiles_per_item) * kNarrowRows;
+  int b, tile;
+  decode_tile(p.rag, p.tiles_per_item, static_cast<int>(blockIdx.x), b, tile);
+  const int t0 = tile * kNarrowRows;
 
   for (int e = threadIdx.x; e < p.k * C * C / 4; e += kNarrowThreads)
     reinterpret_cast<float4*>(ws)[e] = reinterpret_cast<const float4*>(p.w)[e];
@@ -111,22 +112,23 @@ __global__ void __launch_bounds__(kNarrowThreads) conv_narrow_kernel(const Narro
 }
 
 template <int C>
-static cudaError_t launch_narrow_c(const NarrowConvParams& p, cudaStream_t st) {
+static cudaError_t launch_narrow_c(const NarrowConvParams& p, int total_tiles, cudaStream_t st) {
   const int span = (p.k - 1) * p.dil;
   const size_t smem = (static_cast<size_t>(kNarrowRows + span) * (C + 4) + static_cast<size_t>(p.k) * C * C) * sizeof(float);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(conv_narrow_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
   }
-  conv_narrow_kernel<C><<<static_cast<unsigned>(p.B * p.tiles_per_item), kNarrowThreads, smem, st>>>(p);
+  conv_narrow_kernel<C><<<static_cast<unsigned>(total_tiles), kNarrowThreads, smem, st>>>(p);
   return cudaGetLastError();
 }
 
 // C must be 8 or 16; k odd.
-cudaError_t launch_conv_narrow(int c, NarrowConvParams p, cudaStream_t st) {
+cudaError_t launch_conv_narrow(int c, NarrowConvParams p, cudaStream_t st, const RaggedItems* items) {
   p.tiles_per_item = (p.L + kNarrowRows - 1) / kNarrowRows;
-  if (c == 16) return launch_narrow_c<16>(p, st);
-  if (c == 8) return launch_narrow_c<8>(p, st);
+  const int total = ragged_fill(&p.rag, items, p.B, p.L, kNarrowRows);
+  if (c == 16) return launch_narrow_c<16>(p, total, st);
+  if (c == 8) return launch_narrow_c<8>(p, total, st);
   return cudaErrorInvalidValue;
 }
 

@@ -132,8 +132,9 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
     if (lane == 0) {
       for (int i = 0; i < n_my; ++i) {
         const int work = blockIdx.x + i * gridDim.x;
-        const int b = work / p.tiles_per_item;
-        const int m0 = (work - b * p.tiles_per_item) * p.r_out;
+        int b, tile;
+        decode_tile(p.rag, p.tiles_per_item, work, b, tile);
+        const int m0 = tile * p.r_out;
         const int buf = i & 1;
         mbar_wait(&slab_empty[buf], ((i >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&slab_full[buf], slab_bytes);
@@ -238,8 +239,9 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
     // E1: D1 -> (+b1, leaky_relu, bf16) -> xt tile in UMMA layout; two (sub-tile, 16-column) items
     auto e1 = [&](int i) {
       const int work = blockIdx.x + i * gridDim.x;
-      const int b = work / p.tiles_per_item;
-      const int m0 = (work - b * p.tiles_per_item) * p.r_out;
+      int b, tile;
+      decode_tile(p.rag, p.tiles_per_item, work, b, tile);
+      const int m0 = tile * p.r_out;
       const int buf = i & 1;
       const uint32_t ph = (i >> 1) & 1;
       const int tbi = p.t_bufs == 2 ? buf : 0;
@@ -294,8 +296,9 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
     // row is added to it in place, and after the transpose 8 lanes cover one 128-byte row segment.
     auto coords = [&](int i, int& b, int& m0) {
       const int work = blockIdx.x + i * gridDim.x;
-      b = work / p.tiles_per_item;
-      m0 = (work - b * p.tiles_per_item) * p.r_out;
+      int tile;
+      decode_tile(p.rag, p.tiles_per_item, work, b, tile);
+      m0 = tile * p.r_out;
     };
     auto prefetch_res = [&](int i) {  // lane 0 only
       int b, m0;

@@ -142,8 +142,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       int buf = 0; uint32_t phase = 0;
       for (int work = blockIdx.x; work < p.total_work; work += gridDim.x) {
         const int mt = work / p.n_blocks;
-        const int b = mt / p.tiles_per_item;
-        const int m0 = (mt - b * p.tiles_per_item) * (MS * 128);
+        int b, tile;
+        decode_tile(p.rag, p.tiles_per_item, mt, b, tile);
+        const int m0 = tile * (MS * 128);
         for (int c = 0; c < p.nc; ++c) {
           mbar_wait(&slab_empty[buf], phase ^ 1);
           mbar_arrive_expect_tx(&slab_full[buf], PLANES * slab_bytes);
@@ -254,8 +255,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     auto tile_coords = [&](int work, int& nblk, int& b, int& m0) {
       nblk = work % p.n_blocks;
       const int mt = work / p.n_blocks;
-      b = mt / p.tiles_per_item;
-      m0 = (mt - b * p.tiles_per_item) * (MS * 128);
+      int tile;
+      decode_tile(p.rag, p.tiles_per_item, mt, b, tile);
+      m0 = tile * (MS * 128);
     };
     auto prefetch_res = [&](int work, int j) {  // lane 0 only
       int nblk, b, m0;
@@ -381,8 +383,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     for (int work = blockIdx.x; work < p.total_work; work += gridDim.x, ++it) {
       const int nblk = work % p.n_blocks;
       const int mt = work / p.n_blocks;
-      const int b = mt / p.tiles_per_item;
-      const int m0 = (mt - b * p.tiles_per_item) * (MS * 128);
+      int b, tile;
+      decode_tile(p.rag, p.tiles_per_item, mt, b, tile);
+      const int m0 = tile * (MS * 128);
       int ms_count = (p.rows - m0 + 127) / 128;
       ms_count = ms_count > MS ? MS : ms_count;
       const int ab = it & 1;

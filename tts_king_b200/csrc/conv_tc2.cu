@@ -163,8 +163,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
   // pair tile -> (batch item, first row of THIS CTA's 128*MS rows)
   auto tile_coords = [&](int work, int& b, int& m0) {
-    b = work / p.tiles_per_item;
-    m0 = (work - b * p.tiles_per_item) * (2 * MS * 128) + static_cast<int>(rank) * (MS * 128);
+    int tile;
+    decode_tile(p.rag, p.tiles_per_item, work, b, tile);
+    m0 = tile * (2 * MS * 128) + static_cast<int>(rank) * (MS * 128);
   };
 
   if (warp == 0) {

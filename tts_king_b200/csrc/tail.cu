@@ -23,13 +23,15 @@ template <bool VEC4>
 __global__ void __launch_bounds__(kPostTile) conv_post_kernel(const float* __restrict__ x, int L, int C,
                                                               const float* __restrict__ w,  // [7][C] tap-major
                                                               float bias, int tiles_per_item, float* __restrict__ out_f32,
-                                                              int16_t* __restrict__ out_i16, float out_scale) {
+                                                              int16_t* __restrict__ out_i16, float out_scale,
+                                                              const RaggedPrefix rag) {
   extern __shared__ float psm[];
   const int pitch = VEC4 ? C + 4 : C + 1;
   float* xs = psm;                                   // [kPostTile + 6][pitch]
   float* ws = psm + (kPostTile + kPostK - 1) * pitch;  // [7][C]
-  const int b = blockIdx.x / tiles_per_item;
-  const int t0 = (blockIdx.x - b * tiles_per_item) * kPostTile;
+  int b, tile;
+  decode_tile(rag, tiles_per_item, static_cast<int>(blockIdx.x), b, tile);
+  const int t0 = tile * kPostTile;
   const float* xb = x + static_cast<long long>(b) * L * C;
   for (int e = threadIdx.x; e < kPostK * C; e += kPostTile) ws[e] = w[e];
   if (VEC4) {
@@ -91,12 +93,14 @@ struct PostW32 {
 
 __global__ void __launch_bounds__(kPostTile) conv_post32_kernel(const float* __restrict__ x, int L, const PostW32 W,
                                                                 float bias, int tiles_per_item, float* __restrict__ out_f32,
-                                                                int16_t* __restrict__ out_i16, float out_scale) {
+                                                                int16_t* __restrict__ out_i16, float out_scale,
+                                                                const RaggedPrefix rag) {
   constexpr int C = 32, ROWS = kPostTile + kPostK - 1, PITCH = C + 4, PP = 9;
   __shared__ __align__(16) float xs[ROWS * PITCH];
   __shared__ float ps[ROWS * PP];
-  const int b = blockIdx.x / tiles_per_item;
-  const int t0 = (blockIdx.x - b * tiles_per_item) * kPostTile;
+  int b, tile;
+  decode_tile(rag, tiles_per_item, static_cast<int>(blockIdx.x), b, tile);
+  const int t0 = tile * kPostTile;
   const float* xb = x + static_cast<long long>(b) * L * C;
   // stage the window: all of a thread's loads are issued before the first is consumed (the rolled
   // loop had one 16-byte load in flight per thread and ran at 2 TB/s, latency-bound)
@@ -157,27 +161,29 @@ __global__ void __launch_bounds__(kPostTile) conv_post32_kernel(const float* __r
 
 cudaError_t launch_conv_post(const float* x, int B, int L, int C, const float* w_tapmajor, float bias,
                              float* out_f32, int16_t* out_i16, float out_scale, cudaStream_t st,
-                             const float* w_host_tapmajor) {
+                             const float* w_host_tapmajor, const RaggedItems* items) {
   const int tiles = (L + kPostTile - 1) / kPostTile;
+  RaggedPrefix rag;
+  const int total = ragged_fill(&rag, items, B, L, kPostTile);
   if (C == 32 && w_host_tapmajor) {
     PostW32 W;
     for (int j = 0; j < kPostK; ++j)
       for (int c = 0; c < 32; ++c) W.w[j][c] = w_host_tapmajor[j * 32 + c];
-    conv_post32_kernel<<<static_cast<unsigned>(B * tiles), kPostTile, 0, st>>>(x, L, W, bias, tiles, out_f32, out_i16, out_scale);
+    conv_post32_kernel<<<static_cast<unsigned>(total), kPostTile, 0, st>>>(x, L, W, bias, tiles, out_f32, out_i16, out_scale, rag);
     return cudaGetLastError();
   }
   const bool vec = (C & 3) == 0;
   const int pitch = vec ? C + 4 : C + 1;
   const size_t smem = (static_cast<size_t>(kPostTile + kPostK - 1) * pitch + kPostK * C) * sizeof(float);
-  dim3 grid(static_cast<unsigned>(B * tiles));
+  dim3 grid(static_cast<unsigned>(total));
   if (vec) {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(conv_post_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    conv_post_kernel<true><<<grid, kPostTile, smem, st>>>(x, L, C, w_tapmajor, bias, tiles, out_f32, out_i16, out_scale);
+    conv_post_kernel<true><<<grid, kPostTile, smem, st>>>(x, L, C, w_tapmajor, bias, tiles, out_f32, out_i16, out_scale, rag);
   } else {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(conv_post_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    conv_post_kernel<false><<<grid, kPostTile, smem, st>>>(x, L, C, w_tapmajor, bias, tiles, out_f32, out_i16, out_scale);
+    conv_post_kernel<false><<<grid, kPostTile, smem, st>>>(x, L, C, w_tapmajor, bias, tiles, out_f32, out_i16, out_scale, rag);
   }
   return cudaGetLastError();
 }

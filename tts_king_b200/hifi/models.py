@@ -14,7 +14,7 @@ Inference only: the output never requires grad.  CUDA only: a CPU tensor raises.
 from __future__ import annotations
 
 import ctypes
-from typing import Dict, List, Optional, Tuple
+from typing import Sequence, Dict, List, Optional, Tuple
 
 import torch
 import torch.nn as nn
@@ -158,14 +158,25 @@ class _Engine:
         _native.check(self.L.hg_forward_launches(self.plan, B, T, prec, ctypes.byref(n)))
         return n.value
 
-    def forward(self, mel: torch.Tensor, out: torch.Tensor, out_dtype: int, out_scale: float, prec: int):
+    def forward(self, mel: torch.Tensor, out: torch.Tensor, out_dtype: int, out_scale: float, prec: int,
+                frames: Optional[Sequence[int]] = None):
         B, _, T = mel.shape
         with torch.cuda.device(self.device):
             st = torch.cuda.current_stream().cuda_stream
             ws, ws_bytes = self.workspace(B, T, prec, st)
             sB, sC, sT = mel.stride()
-            _native.check(self.L.hg_forward(self.plan, mel.data_ptr(), sB, sC, sT, B, T, out.data_ptr(), out_dtype,
-                                            float(out_scale), prec, ws, ws_bytes, st))
+            if frames is None:
+                _native.check(self.L.hg_forward(self.plan, mel.data_ptr(), sB, sC, sT, B, T, out.data_ptr(), out_dtype,
+                                                float(out_scale), prec, ws, ws_bytes, st))
+            else:
+                fr = (ctypes.c_int32 * B)(*[int(v) for v in frames])
+                _native.check(self.L.hg_forward_ragged(self.plan, mel.data_ptr(), sB, sC, sT, B, T, fr, out.data_ptr(),
+                                                       out_dtype, float(out_scale), prec, ws, ws_bytes, st))
+
+    def halo_frames(self) -> int:
+        n = ctypes.c_int()
+        _native.check(self.L.hg_halo_frames(self.plan, ctypes.byref(n)))
+        return n.value
 
 
     def layer_table(self, prec: int) -> List[_native.HgLayerInfo]:
@@ -254,10 +265,21 @@ class Generator(nn.Module):
 
     # ------------------------------------------------------------------ extensions
     @torch.no_grad()
-    def generate_int16(self, x, max_wav_value: float = 32768.0):
+    def generate_int16(self, x, max_wav_value: float = 32768.0, frames: Optional[Sequence[int]] = None):
         """forward + ``* MAX_WAV_VALUE`` + numpy-style truncating int16 cast, fused into the last
-        kernel (the tail of reference hifiapi.py:47-51).  Returns a device int16 tensor [B,1,N]."""
-        return self._run(x, _native.OUT_I16, float(max_wav_value))
+        kernel (the tail of reference hifiapi.py:47-51).  Returns a device int16 tensor [B,1,N].
+        ``frames``: see ``forward_ragged``."""
+        return self._run(x, _native.OUT_I16, float(max_wav_value), frames)
+
+    @torch.no_grad()
+    def forward_ragged(self, x, frames: Sequence[int]):
+        """``forward`` for a padded batch [B,80,T] (B <= 64) in which utterance ``i`` only keeps its first
+        ``frames[i]`` mel frames (the vocoder call of synth_samples, fs_two/utils/tools.py:257-268).
+        Rows past ``frames[i]`` + the receptive halo (13 frames for V1) are not computed at any
+        layer; the returned [B,1,T*hop] tensor is bit-identical to ``forward(x)`` on
+        ``[i, 0, :frames[i]*hop]`` and zero beyond (from the next multiple of 256 samples on, when hop is
+        not a multiple of the last kernel's 256-sample tile)."""
+        return self._run(x, _native.OUT_F32, 1.0, frames)
 
     @torch.no_grad()
     def make_graphed(self, B: int, T: int, out_int16: bool = False, max_wav_value: float = 32768.0):
@@ -379,7 +401,7 @@ class Generator(nn.Module):
             self._engine_key = key
         return self._engine
 
-    def _run(self, x, out_dtype: int, out_scale: float):
+    def _run(self, x, out_dtype: int, out_scale: float, frames: Optional[Sequence[int]] = None):
         if not isinstance(x, torch.Tensor):
             raise TypeError("expected a Tensor")
         squeeze = x.dim() == 2
@@ -396,7 +418,14 @@ class Generator(nn.Module):
         if x.dtype != torch.float32:
             x = x.float()
         B, _, T = x.shape
-        out = torch.empty((B, 1, T * self.hop_length), device=x.device,
-                          dtype=torch.float32 if out_dtype == _native.OUT_F32 else torch.int16)
-        eng.forward(x, out, out_dtype, out_scale, _native.PRECISIONS[self.precision])
+        if frames is not None:
+            frames = [int(v) for v in (frames.tolist() if hasattr(frames, "tolist") else frames)]
+            if len(frames) != B:
+                raise ValueError(f"{len(frames)} frame counts for a batch of {B}")
+            if B > _native.MAX_RAGGED_ITEMS:
+                raise ValueError(f"a ragged batch holds at most {_native.MAX_RAGGED_ITEMS} utterances, got {B}")
+        alloc = torch.empty if frames is None else torch.zeros  # ragged: the skipped tail reads as silence
+        out = alloc((B, 1, T * self.hop_length), device=x.device,
+                    dtype=torch.float32 if out_dtype == _native.OUT_F32 else torch.int16)
+        eng.forward(x, out, out_dtype, out_scale, _native.PRECISIONS[self.precision], frames)
         return out.squeeze(0) if squeeze else out
