@@ -121,6 +121,42 @@ HG_API int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC, in
                void* out, int out_dtype, float out_scale, int precision, void* workspace,
                size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Conv stacks — the step before the vocoder: FastSpeech2's PostNet
+ * (fs_two/transformer/Layers.py:71-143: 5 x [Conv1d k5 + BatchNorm1d (+ tanh)]) and mel_linear
+ * (fs_two/model/fastspeech2.py:101-104, a k = 1 conv) on the same conv kernels.  A stack is a plain
+ * chain of same-length Conv1d layers; BatchNorm in eval mode is an affine map per channel and is
+ * folded into the conv's weight and bias by the caller before upload.
+ * Build: hg_stack_create -> hg_plan_upload_weight(plan, "<layer index>", ...) per layer ->
+ * hg_plan_finalize; free with hg_plan_destroy.
+ */
+enum { HG_ACT_NONE = 0, HG_ACT_LRELU = 1, HG_ACT_TANH = 2 };
+
+typedef struct HgStackLayer {
+  int32_t c_in, c_out;
+  int32_t k;         /* odd, padding = dilation * (k - 1) / 2 (ConvNorm's default, Layers.py:49-51) */
+  int32_t dilation;
+  int32_t act;       /* HG_ACT_*: applied to this layer's output on its way into the next layer */
+  float slope;       /* HG_ACT_LRELU only */
+} HgStackLayer;
+
+HG_API int hg_stack_create(const HgStackLayer* layers, int n_layers, int device, HgPlan** plan);
+
+HG_API int hg_stack_workspace_bytes(const HgPlan* plan, int B, int T, int precision, size_t* bytes);
+
+/*
+ * y = stack(x) (+ residual) — PostNet.forward (Layers.py:133-143) without its two transposes, and,
+ * with residual = x, the `postnet(output) + output` of fastspeech2.py:104 in the last epilogue.
+ *   x         device fp32, logical shape [B, c_in, T] with ELEMENT strides (sB, sC, sT); the
+ *             time-major [B,T,c_in] tensor FastSpeech2 produces is sB = T*c_in, sC = 1, sT = c_in.
+ *   residual  device fp32 [B][T][c_out] contiguous, or NULL.
+ *   out       device fp32 [B][T][c_out] contiguous (time-major: what tts_king.py:48 transposes and
+ *             hg_forward reads in place through its strides).
+ */
+HG_API int hg_stack_forward(HgPlan* plan, const float* x, int64_t sB, int64_t sC, int64_t sT, int B, int T,
+                     const float* residual, float* out, int precision, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
 /*
  * Mel frames of right context a sample needs (13 for V1): the generator's
  * receptive reach, rounded up to frames.  What hg_forward_ragged adds to every item's length.

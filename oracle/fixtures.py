@@ -74,3 +74,26 @@ def state_digest(state: Dict[str, torch.Tensor]) -> str:
 
 def to_numpy_state(state: Dict[str, torch.Tensor]) -> Dict[str, np.ndarray]:
     return {k: v.detach().cpu().numpy() for k, v in state.items()}
+
+
+# ----------------------------------------------------------------------------- PostNet (N3)
+POSTNET_FULL = dict(n_mel_channels=80, postnet_embedding_dim=512, postnet_kernel_size=5, postnet_n_convolutions=5)
+POSTNET_TINY = dict(n_mel_channels=80, postnet_embedding_dim=32, postnet_kernel_size=5, postnet_n_convolutions=5)
+
+
+def alive_batchnorm_(state: Dict[str, torch.Tensor], seed: int = 97) -> Dict[str, torch.Tensor]:
+    """Give every BatchNorm of a PostNet state dict trained-like statistics, in place and seeded: a
+    fresh BatchNorm1d (mean 0, var 1, gamma 1, beta 0) would make the eval-mode fold a no-op and
+    hide mistakes in it.  Conv weights are rescaled so activations stay O(1) through the tanh's."""
+    g = torch.Generator().manual_seed(seed)
+    i = 0
+    while f"convolutions.{i}.1.running_mean" in state:
+        c = state[f"convolutions.{i}.1.running_mean"].numel()
+        state[f"convolutions.{i}.1.running_mean"] = torch.randn(c, generator=g) * 0.2
+        state[f"convolutions.{i}.1.running_var"] = torch.rand(c, generator=g) + 0.5
+        state[f"convolutions.{i}.1.weight"] = torch.rand(c, generator=g) + 0.5
+        state[f"convolutions.{i}.1.bias"] = torch.randn(c, generator=g) * 0.1
+        w = state[f"convolutions.{i}.0.conv.weight"]
+        state[f"convolutions.{i}.0.conv.weight"] = w * (1.5 / (w.std() * (w.shape[1] * w.shape[2]) ** 0.5))
+        i += 1
+    return state

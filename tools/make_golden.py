@@ -43,8 +43,76 @@ def import_reference():
     return ref_models, ref_api
 
 
+def import_reference_postnet():
+    """fs_two/transformer/Layers.py on its own: the package __init__ pulls in text front-ends whose
+    dependencies (unidecode, ...) are not installed, and Layers.py itself only needs torch plus the
+    two attention classes of SubLayers for FFTBlock, which PostNet does not touch."""
+    import importlib.util
+
+    pkg = types.ModuleType("_ref_transformer")
+    pkg.__path__ = []
+    sys.modules["_ref_transformer"] = pkg
+    sub = types.ModuleType("_ref_transformer.SubLayers")
+    sub.MultiHeadAttention = object
+    sub.PositionwiseFeedForward = object
+    sys.modules["_ref_transformer.SubLayers"] = sub
+    spec = importlib.util.spec_from_file_location("_ref_transformer.Layers", os.path.join(REF, "fs_two", "transformer", "Layers.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["_ref_transformer.Layers"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make_postnet_golden(out_dir):
+    """tests/golden/postnet.npz — the reference's PostNet (fs_two/transformer/Layers.py:71-143) in eval
+    mode and the mel_linear + postnet + add tail of fs_two/model/fastspeech2.py:101-104."""
+    from oracle import fixtures as fx
+
+    ref_layers = import_reference_postnet()
+    blob = {}
+    # full size (80 -> 512 x3 -> 80): weights are seeded, not stored; their digest is
+    torch.manual_seed(1234)
+    full = ref_layers.PostNet(**fx.POSTNET_FULL)
+    blob["full.digest_fresh"] = np.array(fx.state_digest({k: v for k, v in full.state_dict().items() if v.dtype.is_floating_point}))
+    sd = fx.alive_batchnorm_({k: v.clone() for k, v in full.state_dict().items()})
+    full.load_state_dict(sd)
+    full.eval()
+    blob["full.digest_alive"] = np.array(fx.state_digest({k: v for k, v in sd.items() if v.dtype.is_floating_point}))
+    torch.manual_seed(77)
+    lin = torch.nn.Linear(256, 80)  # fastspeech2.py:26-30
+    torch.nn.init.xavier_normal_(lin.weight)
+    dec = torch.randn(3, 41, 256, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        output = lin(dec)
+        post = full(output)
+        blob["full.lin_w"], blob["full.lin_b"] = lin.weight.detach().numpy(), lin.bias.detach().numpy()
+        blob["full.decoder_output"] = dec.numpy()
+        blob["full.output"] = output.numpy()
+        blob["full.postnet"] = post.numpy()
+        blob["full.postnet_output"] = (post + output).numpy()
+        x1 = torch.randn(1, 1, 80, generator=torch.Generator().manual_seed(6))
+        blob["full.x_T1"], blob["full.y_T1"] = x1.numpy(), full(x1).numpy()
+    # tiny (80 -> 32 x3 -> 80): state dict stored, for load_state_dict parity
+    torch.manual_seed(4321)
+    tiny = ref_layers.PostNet(**fx.POSTNET_TINY)
+    sd = fx.alive_batchnorm_({k: v.clone() for k, v in tiny.state_dict().items()}, seed=98)
+    tiny.load_state_dict(sd)
+    tiny.eval()
+    for k, v in sd.items():
+        blob["tiny.sd." + k] = v.numpy()
+    x = torch.randn(2, 23, 80, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        blob["tiny.x"], blob["tiny.y"] = x.numpy(), tiny(x).numpy()
+    np.savez_compressed(os.path.join(out_dir, "postnet.npz"), **blob)
+    print("postnet.npz:", {k: getattr(v, "shape", None) for k, v in blob.items() if not k.startswith("tiny.sd.")})
+
+
 def main():
     from oracle import fixtures as fx
+
+    if "--postnet-only" in sys.argv:
+        make_postnet_golden(os.path.join(ROOT, "tests", "golden"))
+        return
 
     ref_models, ref_api = import_reference()
     out_dir = os.path.join(ROOT, "tests", "golden")
@@ -140,6 +208,7 @@ def main():
         warnings.simplefilter("ignore")
         edge_i16 = (torch.from_numpy(edge) * 32768).numpy().astype("int16")
     np.savez_compressed(os.path.join(out_dir, "int16_cast.npz"), x=edge, y=edge_i16)
+    make_postnet_golden(out_dir)
     print("hifiapi", wav_i16.shape, wav_i16.dtype, int(np.abs(wav_i16).max()), "edge", edge_i16.tolist())
 
 

@@ -38,6 +38,12 @@ class HgLayerInfo(ctypes.Structure):
         "stages", "smem_bytes", "weights_resident", "slab_buffers")]
 
 
+class HgStackLayer(ctypes.Structure):
+    _fields_ = [("c_in", ctypes.c_int32), ("c_out", ctypes.c_int32), ("k", ctypes.c_int32), ("dilation", ctypes.c_int32),
+                ("act", ctypes.c_int32), ("slope", ctypes.c_float)]
+
+
+ACT_NONE, ACT_LRELU, ACT_TANH = 0, 1, 2  # HG_ACT_*
 MAX_RAGGED_ITEMS = 64  # kMaxRaggedItems, csrc/common.cuh (hg_forward_ragged's bound on B)
 
 
@@ -71,6 +77,9 @@ def lib() -> ctypes.CDLL:
     L.hg_forward.argtypes = [vp, vp, i64, i64, i64, i, i, vp, i, f, i, vp, sz, vp]
     L.hg_halo_frames.argtypes = [vp, ctypes.POINTER(i)]
     L.hg_forward_ragged.argtypes = [vp, vp, i64, i64, i64, i, i, ctypes.POINTER(ctypes.c_int32), vp, i, f, i, vp, sz, vp]
+    L.hg_stack_create.argtypes = [ctypes.POINTER(HgStackLayer), i, i, ctypes.POINTER(vp)]
+    L.hg_stack_workspace_bytes.argtypes = [vp, i, i, i, ctypes.POINTER(sz)]
+    L.hg_stack_forward.argtypes = [vp, vp, i64, i64, i64, i, i, vp, vp, i, vp, sz, vp]
     L.hg_plan_destroy.argtypes = [vp]
     L.hg_op_conv1d.argtypes = [i, i, vp, i, i, i, vp, vp, i, i, i, f, vp, vp, vp]
     L.hg_op_conv_transpose1d.argtypes = [i, i, vp, i, i, i, vp, vp, i, i, i, f, vp, vp]
@@ -82,7 +91,8 @@ def lib() -> ctypes.CDLL:
     L.hg_profile_forward.argtypes = [vp, vp, i64, i64, i64, i, i, vp, i, f, i, vp, sz, vp, ctypes.POINTER(i),
                                      ctypes.POINTER(f), i, ctypes.POINTER(i)]
     for name in ("hg_plan_create", "hg_plan_upload_weight", "hg_plan_finalize", "hg_workspace_bytes",
-                 "hg_forward_launches", "hg_forward", "hg_halo_frames", "hg_forward_ragged", "hg_plan_destroy", "hg_op_conv1d",
+                 "hg_forward_launches", "hg_forward", "hg_halo_frames", "hg_forward_ragged", "hg_stack_create",
+                 "hg_stack_workspace_bytes", "hg_stack_forward", "hg_plan_destroy", "hg_op_conv1d",
                  "hg_op_conv_transpose1d", "hg_op_conv_post", "hg_op_conv_pair", "hg_selftest_tcgen05", "hg_layer_count",
                  "hg_layer_info",
                  "hg_profile_forward"):

@@ -23,7 +23,7 @@ cudaError_t launch_conv_post(const float* x, int B, int L, int C, const float* w
                              int16_t* out_i16, float out_scale, cudaStream_t st, const float* w_host_tapmajor,
                              const RaggedItems* items = nullptr);
 cudaError_t launch_mel_to_operand(const float* mel, long long sB, long long sC, long long sT, int B, int C, int T,
-                                  int c_pad, int a_fmt, void* a0, void* a1, cudaStream_t st);
+                                  int c_pad, int a_fmt, void* a0, void* a1, cudaStream_t st, int act = 0, float slope = 1.f);
 cudaError_t launch_f32_to_operand(const float* x, long long n, float slope, int a_fmt, void* a0, void* a1,
                                   cudaStream_t st);
 int run_tcgen05_selftest(char* buf, size_t len);
@@ -871,6 +871,7 @@ static int layout_workspace(const HgPlan* plan, int B, int T, int precision, voi
 
 static int check_fwd_args(const HgPlan* plan, int B, int T, int precision) {
   if (!plan) return fail(HG_EINVAL, "null plan");
+  if (plan->is_stack) return fail(HG_ESTATE, "this plan is a conv stack (hg_stack_create): use hg_stack_forward");
   if (!plan->finalized) return fail(HG_ESTATE, "plan not finalized");
   if (B < 1 || T < 1) return fail(HG_EINVAL, "expected B >= 1 and T >= 1, got B=%d T=%d", B, T);
   if (precision < HG_PREC_BF16 || precision > HG_PREC_FP32_FFMA) return fail(HG_EINVAL, "unknown precision %d", precision);
@@ -1041,6 +1042,132 @@ extern "C" int hg_forward_ragged(HgPlan* plan, const float* mel, int64_t sB, int
   const int rc = hg_forward(plan, mel, sB, sC, sT, B, T, out, out_dtype, out_scale, precision, workspace, workspace_bytes, stream);
   g_rag = nullptr;
   return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv stacks: FastSpeech2's PostNet (fs_two/transformer/Layers.py:71-143, BatchNorm folded by the
+// caller) and mel_linear (fs_two/model/fastspeech2.py:101-104) on the generator's conv kernels
+static void init_plan_env(HgPlan* p, int device) {
+  p->device = device;
+  cudaDeviceProp pr;
+  if (cudaGetDeviceProperties(&pr, device) == cudaSuccess) p->sm_count = pr.multiProcessorCount;
+  p->desc_mode = env_int("HG_DESC_MODE", 0);
+  p->force_ms = env_int("HG_TC_MS", 0);
+  p->force_stages = env_int("HG_TC_STAGES", 0);
+  p->force_ffma = env_int("HG_FORCE_FFMA", 0) != 0;
+  p->ctas_per_sm = env_int("HG_TC_CTAS_PER_SM", 1);
+  p->fuse_pairs = env_int("HG_FUSE_PAIRS", 1) != 0;
+  p->epi_tma = env_int("HG_EPI_TMA", 1) != 0;
+  p->use_tc2 = env_int("HG_TC2", 1) != 0;
+}
+
+extern "C" int hg_stack_create(const HgStackLayer* layers, int n_layers, int device, HgPlan** out) {
+  if (!layers || !out) return fail(HG_EINVAL, "null argument");
+  *out = nullptr;
+  if (n_layers < 1 || n_layers > 64) return fail(HG_EINVAL, "a stack holds 1..64 layers, got %d", n_layers);
+  for (int i = 0; i < n_layers; ++i) {
+    const HgStackLayer& d = layers[i];
+    if (d.c_in < 1 || d.c_out < 1 || d.k < 1 || d.k > kMaxTaps || (d.k & 1) == 0 || d.dilation < 1)
+      return fail(HG_EINVAL, "stack layer %d: bad shape (odd k <= %d, dilation >= 1)", i, kMaxTaps);
+    if (d.act < HG_ACT_NONE || d.act > HG_ACT_TANH) return fail(HG_EINVAL, "stack layer %d: unknown activation %d", i, d.act);
+    if (i + 1 < n_layers && layers[i + 1].c_in != d.c_out)
+      return fail(HG_EINVAL, "stack layer %d takes %d channels but layer %d produces %d", i + 1, layers[i + 1].c_in, i, d.c_out);
+  }
+  if (layers[n_layers - 1].act != HG_ACT_NONE) return fail(HG_EINVAL, "the last layer's output is returned as is: act must be HG_ACT_NONE");
+  int rc = check_device(device);
+  if (rc) return rc;
+  HgPlan* p = new HgPlan();
+  memset(&p->cfg, 0, sizeof(p->cfg));
+  p->is_stack = true;
+  init_plan_env(p, device);
+  for (int i = 0; i < n_layers; ++i) {
+    p->layers.push_back(make_conv(std::to_string(i), layers[i].c_in, layers[i].c_out, layers[i].k, layers[i].dilation));
+    p->stack_act.push_back(layers[i].act);
+    p->stack_slope.push_back(layers[i].slope);
+    p->by_name[p->layers.back().name] = i;
+  }
+  *out = p;
+  return HG_OK;
+}
+
+struct StackWorkspace {
+  OperandBuf A;
+  float* F;
+  size_t bytes;
+};
+
+static int in_pitch(const HgPlan* plan, const Layer& l, int precision) { return use_tc(plan, l, precision) ? l.cin_pad : l.cin; }
+
+static void layout_stack(const HgPlan* plan, int B, int T, int precision, void* base, StackWorkspace* ws) {
+  size_t max_a = 0, max_f = 0;
+  for (const Layer& l : plan->layers) {
+    max_a = std::max(max_a, static_cast<size_t>(B) * T * in_pitch(plan, l, precision));
+    max_f = std::max(max_f, static_cast<size_t>(B) * T * l.cout);
+  }
+  const size_t plane = align_up(max_a * 2, 1024);
+  const size_t ab = precision == HG_PREC_BF16 ? plane : precision == HG_PREC_FP32 ? 2 * plane : align_up(max_a * 4, 1024);
+  uint8_t* p = static_cast<uint8_t*>(base);
+  ws->A.a0 = p;
+  ws->A.a1 = precision == HG_PREC_FP32 ? p + plane : nullptr;
+  ws->F = reinterpret_cast<float*>(p + ab);
+  ws->bytes = ab + align_up(max_f * 4, 1024);
+}
+
+static int check_stack_args(const HgPlan* plan, int B, int T, int precision) {
+  if (!plan) return fail(HG_EINVAL, "null plan");
+  if (!plan->is_stack) return fail(HG_ESTATE, "this plan is a generator (hg_plan_create): use hg_forward");
+  if (!plan->finalized) return fail(HG_ESTATE, "plan not finalized");
+  if (B < 1 || T < 1) return fail(HG_EINVAL, "expected B >= 1 and T >= 1, got B=%d T=%d", B, T);
+  if (precision < HG_PREC_BF16 || precision > HG_PREC_FP32_FFMA) return fail(HG_EINVAL, "unknown precision %d", precision);
+  return HG_OK;
+}
+
+extern "C" int hg_stack_workspace_bytes(const HgPlan* plan, int B, int T, int precision, size_t* bytes) {
+  int rc = check_stack_args(plan, B, T, precision);
+  if (rc) return rc;
+  if (!bytes) return fail(HG_EINVAL, "null bytes");
+  StackWorkspace ws;
+  layout_stack(plan, B, T, precision, nullptr, &ws);
+  *bytes = ws.bytes;
+  return HG_OK;
+}
+
+extern "C" int hg_stack_forward(HgPlan* plan, const float* x, int64_t sB, int64_t sC, int64_t sT, int B, int T,
+                                const float* residual, float* out, int precision, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  int rc = check_stack_args(plan, B, T, precision);
+  if (rc) return rc;
+  if (!x || !out || !workspace) return fail(HG_EINVAL, "null buffer");
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(HG_EINVAL, "workspace must be 1024-byte aligned");
+  StackWorkspace ws;
+  layout_stack(plan, B, T, precision, workspace, &ws);
+  if (workspace_bytes < ws.bytes) return fail(HG_ENOMEM, "workspace too small: %zu < %zu bytes", workspace_bytes, ws.bytes);
+  CUDA_TRY(cudaSetDevice(plan->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int fmt = a_fmt_of(precision);
+  const int n = static_cast<int>(plan->layers.size());
+  // x [B, C, T] (any strides; a time-major [B,T,C] tensor is sC = 1, sT = C) -> operand of layer 0
+  cudaError_t e = launch_mel_to_operand(x, sB, sC, sT, B, plan->layers[0].cin, T, in_pitch(plan, plan->layers[0], precision), fmt,
+                                        ws.A.a0, ws.A.a1, st);
+  if (e != cudaSuccess) return fail(HG_ECUDA, "stack input repack: %s", cudaGetErrorString(e));
+  for (int i = 0; i < n; ++i) {
+    const Layer& l = plan->layers[i];
+    const bool last = i == n - 1;
+    EpiParams ep; memset(&ep, 0, sizeof(ep));
+    ep.slope = 1.f;
+    ep.out_x = last ? out : ws.F;
+    ep.res = last ? residual : nullptr;
+    if ((rc = run_layer(plan, l, precision, B, T, ws.A, ep, st))) return rc;
+    if (!last) {
+      // activation between the layers + operand format of the next one (a pass over B*T*C floats:
+      // the stack is ~1 % of the vocoder's work, so this is not fused into the conv epilogues)
+      const Layer& nx = plan->layers[i + 1];
+      e = launch_mel_to_operand(ws.F, static_cast<long long>(T) * l.cout, 1, l.cout, B, l.cout, T, in_pitch(plan, nx, precision), fmt,
+                                ws.A.a0, ws.A.a1, st, plan->stack_act[i], plan->stack_slope[i]);
+      if (e != cudaSuccess) return fail(HG_ECUDA, "stack activation (layer %d): %s", i, cudaGetErrorString(e));
+    }
+  }
+  return HG_OK;
 }
 
 extern "C" int hg_layer_count(const HgPlan* plan, int* count) {

@@ -64,6 +64,11 @@ struct HgPlan {
   bool epi_tma = true;     // HG_EPI_TMA=0: always use the generic (LSU) epilogue in conv_tc
   bool use_tc2 = true;     // HG_TC2=0: never use the CTA-pair (cta_group::2) kernel for the 256/128-channel convs
   bool force_ffma = false;  // HG_FORCE_FFMA=1: route every layer to the CUDA-core kernel
+  // hg_stack_create: a plain chain of same-length Conv1d layers (no generator schedule); act/slope[i] is
+  // the activation between layer i and layer i+1
+  bool is_stack = false;
+  std::vector<int> stack_act;
+  std::vector<float> stack_slope;
   std::mutex mu;
   std::map<hg::MapKey, CUtensorMap> maps;
 };

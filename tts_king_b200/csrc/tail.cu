@@ -189,8 +189,11 @@ cudaError_t launch_conv_post(const float* x, int B, int L, int C, const float* w
 }
 
 // mel [B, C, T] with element strides (sB, sC, sT)  ->  operand planes [B][T][c_pad], zero padded.
+// act: 0 none, 1 leaky_relu(slope), 2 tanh — the activation between two layers of a conv stack
+// (hg_stack_forward; the generator's own leaky_relus are fused into its conv epilogues instead).
 __global__ void mel_to_operand_kernel(const float* __restrict__ mel, long long sB, long long sC, long long sT, int B,
-                                      int C, int T, int c_pad, int a_fmt, void* __restrict__ a0, void* __restrict__ a1) {
+                                      int C, int T, int c_pad, int a_fmt, void* __restrict__ a0, void* __restrict__ a1,
+                                      int act, float slope) {
   const long long total = static_cast<long long>(B) * T * c_pad;
   for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
        e += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -198,7 +201,9 @@ __global__ void mel_to_operand_kernel(const float* __restrict__ mel, long long s
     const long long bt = e / c_pad;
     const int t = static_cast<int>(bt % T);
     const int b = static_cast<int>(bt / T);
-    const float v = c < C ? mel[b * sB + c * sC + t * sT] : 0.f;
+    float v = c < C ? mel[b * sB + c * sC + t * sT] : 0.f;
+    if (act == 1) v = lrelu(v, slope);
+    else if (act == 2) v = tanhf(v);
     if (a_fmt == A_F32) {
       static_cast<float*>(a0)[e] = v;
     } else {
@@ -210,10 +215,10 @@ __global__ void mel_to_operand_kernel(const float* __restrict__ mel, long long s
 }
 
 cudaError_t launch_mel_to_operand(const float* mel, long long sB, long long sC, long long sT, int B, int C, int T,
-                                  int c_pad, int a_fmt, void* a0, void* a1, cudaStream_t st) {
+                                  int c_pad, int a_fmt, void* a0, void* a1, cudaStream_t st, int act, float slope) {
   const long long total = static_cast<long long>(B) * T * c_pad;
   const int blocks = static_cast<int>((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
-  mel_to_operand_kernel<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(mel, sB, sC, sT, B, C, T, c_pad, a_fmt, a0, a1);
+  mel_to_operand_kernel<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(mel, sB, sC, sT, B, C, T, c_pad, a_fmt, a0, a1, act, slope);
   return cudaGetLastError();
 }
 
