@@ -81,6 +81,26 @@ def main():
                               "audio_s": audio_s, "audio_sec_per_sec": audio_s / (ms * 1e-3),
                               "frames_per_rank_max": max(sum(lengths[i] for i in s) for s in parallel.shard_utterances(lengths, world))}))
 
+    # ---------------- cfg-3 ragged again, the way synth_samples batches it (padded to the longest item), with the
+    # padding skipped inside the kernels (Generator.forward_ragged) — one forward per rank
+    lengths = np.random.default_rng(3).integers(400, 2001, size=64).tolist()
+    mine = parallel.shard_utterances(lengths, world)[rank]
+    fr = [lengths[i] for i in mine]
+    padded = torch.zeros(len(mine), 80, max(fr))
+    for row, L in enumerate(fr):
+        padded[row, :, :L] = torch.randn(80, L, generator=torch.Generator().manual_seed(L))
+    padded = padded.to(dev)
+
+    def run_ragged():
+        return m.forward_ragged(padded, fr)
+
+    run_ragged()
+    ms, _ = timed(run_ragged, dev, world)
+    if rank == 0:
+        audio_s = sum(lengths) * HOP / SR
+        print(json.dumps({"config": "cfg3_ragged_padded_batch_kernel_skip", "n_gpus": world, "precision": args.precision, "ms": ms,
+                          "audio_s": audio_s, "audio_sec_per_sec": audio_s / (ms * 1e-3)}))
+
     # ---------------- cfg-5: one 60-minute mel, time-chunked with halo exchange
     if not args.skip_long:
         T = 310078

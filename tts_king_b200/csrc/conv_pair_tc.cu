@@ -35,7 +35,9 @@ constexpr int kPairEpiWarps = 16;
 constexpr int kPairThreads = (3 + kPairEpiWarps) * 32;
 constexpr int kPairStageFloats = 32 * 32;        // per-warp transpose tile: 32 rows x 32 fp32 columns
 
-template <int C, int MS>
+// DBG = true is the HG_TC_DEBUG_TIMING build of the same kernel (cycle counters around every wait);
+// the production instantiation carries none of it.
+template <int C, int MS, bool DBG>
 __global__ void __launch_bounds__(kPairThreads, 1)
 conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_res,
                     const TcPairParams p) {
@@ -154,10 +156,10 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
     int stage = 0; uint32_t wphase = 0;
     bool w_seen = false;  // resident mode: every stage has been waited for once
     // bring-up instrumentation (HG_TC_DEBUG_TIMING): cycles spent in each wait, kept in global memory
-    long long* dbg = p.dbg ? p.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
-    const long long c_t0 = dbg ? clock64() : 0;
+    long long* dbg = (DBG && p.dbg) ? p.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
+    const long long c_t0 = (DBG && dbg) ? clock64() : 0;
     auto timed_wait = [&](uint64_t* bar, uint32_t ph, int slot) {
-      if (dbg) { const long long t0 = clock64(); mbar_wait(bar, ph); if (lane == 0) dbg[slot] += clock64() - t0; }
+      if (DBG && dbg) { const long long t0 = clock64(); mbar_wait(bar, ph); if (lane == 0) dbg[slot] += clock64() - t0; }
       else mbar_wait(bar, ph);
     };
 
@@ -215,7 +217,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
       g2(i);
       w_seen = true;
     }
-    if (dbg && lane == 0) { dbg[0] = clock64() - c_t0; dbg[6] = n_my; }
+    if (DBG && dbg && lane == 0) { dbg[0] = clock64() - c_t0; dbg[6] = n_my; }
   } else {
     // ------------------------------------------------ epilogue warps (all 16 do E1 then E2)
     const int e = warp - 3;
@@ -229,10 +231,10 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
     const int ms2 = sub / E2_CH, c02 = (sub - ms2 * E2_CH) * 32;
     const int n2 = c02 + c4 * 4;
     // bring-up instrumentation (HG_TC_DEBUG_TIMING): cycles spent in each wait, kept in global memory
-    long long* dbg = (p.dbg && e == 0) ? p.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
-    const long long c_t0 = dbg ? clock64() : 0;
+    long long* dbg = (DBG && p.dbg && e == 0) ? p.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
+    const long long c_t0 = (DBG && dbg) ? clock64() : 0;
     auto timed_wait = [&](uint64_t* bar, uint32_t ph, int slot) {
-      if (dbg) { const long long t0 = clock64(); mbar_wait(bar, ph); if (lane == 0) dbg[slot] += clock64() - t0; }
+      if (DBG && dbg) { const long long t0 = clock64(); mbar_wait(bar, ph); if (lane == 0) dbg[slot] += clock64() - t0; }
       else mbar_wait(bar, ph);
     };
 
@@ -249,7 +251,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
       timed_wait(&d1_full[buf], ph, 9);
       timed_wait(&t_empty[tbi], tph ^ 1, 10);  // the G2 that last read this xt buffer has retired
       tc_fence_after();
-      const long long c_s = dbg ? clock64() : 0;
+      const long long c_s = (DBG && dbg) ? clock64() : 0;
       uint8_t* tb = tbuf + tbi * t_bytes;
       const uint32_t tmem_acc = tmem_base + buf * ACC_COLS + lane_base;
       constexpr int ITEMS = MS * (N_T / 16);
@@ -287,7 +289,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
       fence_proxy_async();  // generic-proxy writes of xt -> visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_full[tbi]);
-      if (dbg && lane == 0) dbg[13] += clock64() - c_s;
+      if (DBG && dbg && lane == 0) dbg[13] += clock64() - c_s;
     };
 
     // E2: D2 + residual -> smem transpose -> fused epilogue of c2.  The fp32 residual tile of this
@@ -312,7 +314,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
       const int buf = i & 1;
       timed_wait(&d2_full[buf], (i >> 1) & 1, 11);
       tc_fence_after();
-      const long long c_s = dbg ? clock64() : 0;
+      const long long c_s = (DBG && dbg) ? clock64() : 0;
       {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (2 + buf) * ACC_COLS + lane_base + ms2 * N_T + c02, r);
@@ -343,7 +345,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
       if (lane == 0 && i + 1 < n_my) prefetch_res(i + 1);
       epilogue_rows<8, false>(p.epi, b, static_cast<long long>(m0) + ms2 * 128 + quarter * 32 + rsub, 4, n2, v,
                        static_cast<long long>(m0) + p.r_out);
-      if (dbg && lane == 0) dbg[14] += clock64() - c_s;
+      if (DBG && dbg && lane == 0) dbg[14] += clock64() - c_s;
     };
     if (n_my > 0) {
       if (lane == 0) prefetch_res(0);
@@ -353,7 +355,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
       if (i + 1 < n_my) e1(i + 1);
       e2(i);
     }
-    if (dbg && lane == 0) dbg[8] = clock64() - c_t0;
+    if (DBG && dbg && lane == 0) dbg[8] = clock64() - c_t0;
   }
 
   tc_fence_before();
@@ -368,10 +370,10 @@ size_t conv_pair_smem_bytes(int c, int slab_rows, int t_rows, int t_bufs, int st
          static_cast<size_t>(stages) * c * rowb + kPairEpiWarps * kPairStageFloats * 4 + (32 + 2 * stages) * 8 + 16;
 }
 
-template <int C, int MS>
+template <int C, int MS, bool DBG>
 static cudaError_t launch_pair(const CUtensorMap& m, const CUtensorMap& mr, const TcPairParams& p, size_t smem, int grid,
                                cudaStream_t st) {
-  auto kern = conv_pair_tc_kernel<C, MS>;
+  auto kern = conv_pair_tc_kernel<C, MS, DBG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
@@ -389,8 +391,8 @@ static cudaError_t launch_pair(const CUtensorMap& m, const CUtensorMap& mr, cons
 
 cudaError_t launch_conv_pair_tc(int c, const CUtensorMap& m, const CUtensorMap& mr, const TcPairParams& p, size_t smem,
                                 int grid, cudaStream_t st) {
-  if (c == 64) return launch_pair<64, 2>(m, mr, p, smem, grid, st);
-  if (c == 32) return launch_pair<32, 4>(m, mr, p, smem, grid, st);
+  if (c == 64) return p.dbg ? launch_pair<64, 2, true>(m, mr, p, smem, grid, st) : launch_pair<64, 2, false>(m, mr, p, smem, grid, st);
+  if (c == 32) return p.dbg ? launch_pair<32, 4, true>(m, mr, p, smem, grid, st) : launch_pair<32, 4, false>(m, mr, p, smem, grid, st);
   return cudaErrorInvalidValue;
 }
 

@@ -47,7 +47,9 @@ __device__ __forceinline__ uint32_t desc_base_offset(uint32_t saddr, int desc_mo
 // items (item -> batch item b, M tile, N block).  Accumulators are double-buffered in TMEM so the
 // epilogue of item i overlaps the MMAs of item i+1; the slab and weight rings run ahead across
 // item boundaries.
-template <int N_T, int KC, int MS, bool SPLIT>
+// DBG = true: the HG_TC_DEBUG_TIMING build (cycle counters around the MMA warp's waits); instantiated
+// for the bf16 tilings the generator uses, the production kernels carry no clock reads.
+template <int N_T, int KC, int MS, bool SPLIT, bool DBG>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_x,
@@ -174,27 +176,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     int buf = 0; uint32_t sphase = 0;
     int it = 0;
     long long t_acc = 0, t_slab = 0, t_w = 0;
-    const long long t_begin = clock64();
+    const long long t_begin = DBG ? clock64() : 0;
     for (int work = blockIdx.x; work < p.total_work; work += gridDim.x, ++it) {
       const int ab = it & 1;
-      long long tq = clock64();
+      long long tq = DBG ? clock64() : 0;
       mbar_wait(&acc_empty[ab], ((it >> 1) & 1) ^ 1);  // epilogue drained this accumulator buffer
-      t_acc += clock64() - tq;
+      if (DBG) t_acc += clock64() - tq;
       tc_fence_after();
       const uint32_t tmem_acc = tmem_u + ab * ACC_COLS;
       for (int c = 0; c < p.nc; ++c) {
-        tq = clock64();
+        if (DBG) tq = clock64();
         mbar_wait(&slab_full[buf], sphase);
-        t_slab += clock64() - tq;
+        if (DBG) t_slab += clock64() - tq;
         tc_fence_after();
         for (int t = 0; t < p.ntaps; ++t) {
           const uint32_t tap_lo = (static_cast<uint32_t>(p.tap_row[t]) * ROWB) >> 4;
 #pragma unroll
           for (int wp = 0; wp < PLANES; ++wp) {
             if (!p.w_resident || it == 0) {
-              tq = clock64();
+              if (DBG) tq = clock64();
               mbar_wait(&w_full[stage], wphase);
-              t_w += clock64() - tq;
+              if (DBG) t_w += clock64() - tq;
               tc_fence_after();
             }
             const uint32_t b_lo = wst_lo + static_cast<uint32_t>(stage) * (STAGE_BYTES >> 4);
@@ -230,7 +232,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       if (elect_one()) umma_commit(&acc_full[ab]);
       __syncwarp();
     }
-    if (p.dbg && lane == 0) {
+    if (DBG && p.dbg && lane == 0) {
       long long* d = p.dbg + static_cast<size_t>(blockIdx.x) * 8;
       d[0] = clock64() - t_begin; d[1] = t_acc; d[2] = t_slab; d[3] = t_w; d[4] = it;
     }
@@ -446,10 +448,10 @@ size_t conv_tc_smem_bytes(int n_t, int kc, bool split, int slab_rows, int nbuf, 
          (28 + 2 * stages) * 8 + 16;
 }
 
-template <int N_T, int KC, int MS, bool SPLIT>
+template <int N_T, int KC, int MS, bool SPLIT, bool DBG = false>
 static cudaError_t launch_one(const CUtensorMap* maps, const TcConvParams& p, int n_blocks, size_t smem, int grid_ctas,
                               cudaStream_t st) {
-  auto kern = conv_tc_kernel<N_T, KC, MS, SPLIT>;
+  auto kern = conv_tc_kernel<N_T, KC, MS, SPLIT, DBG>;
   static size_t configured = 0;  // per-instantiation high-water mark
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -481,6 +483,12 @@ static cudaError_t launch_split(bool split, const CUtensorMap* maps, const TcCon
 // maps: [0] operand hi, [1] operand lo, [2] residual (fp32), [3] x out (fp32), [4] a_hi out, [5] a_lo out
 cudaError_t launch_conv_tc(int n_t, int kc, int ms, bool split, const CUtensorMap* maps, const TcConvParams& p,
                            int n_blocks, size_t smem, int grid_ctas, cudaStream_t st) {
+  if (p.dbg && !split) {  // instrumented builds of the bf16 tilings of the generator (bring-up only)
+#define HG_DBG_CASE(NT, KCV, MSV) \
+  if (n_t == NT && kc == KCV && ms == MSV) return launch_one<NT, KCV, MSV, false, true>(maps, p, n_blocks, smem, grid_ctas, st);
+    HG_DBG_CASE(256, 64, 1) HG_DBG_CASE(128, 64, 2) HG_DBG_CASE(128, 64, 1) HG_DBG_CASE(64, 64, 2) HG_DBG_CASE(32, 64, 4)
+#undef HG_DBG_CASE
+  }
 #define HG_CASE(NT, KCV, MSV) \
   if (n_t == NT && kc == KCV && ms == MSV) return launch_split<NT, KCV, MSV>(split, maps, p, n_blocks, smem, grid_ctas, st);
   HG_CASE(256, 64, 1)
