@@ -227,9 +227,25 @@ typedef struct HgLayerInfo {
   int32_t tensor_core; /* 1: tcgen05 path available for this layer */
   int32_t n_tile, k_chunk, m_subtiles, stages, smem_bytes; /* tcgen05 tiling at `precision` */
   int32_t weights_resident, slab_buffers;
+  int32_t kernel_path; /* HG_PATH_*: filled by hg_profile_launch_info (what the launch actually ran) */
 } HgLayerInfo;
+enum {
+  HG_PATH_CUDA_CORE = 0,   /* conv_ffma.cu */
+  HG_PATH_TC = 1,          /* conv_tc.cu: tcgen05, one CTA per tile */
+  HG_PATH_TC_CTA_PAIR = 2, /* conv_tc2.cu: tcgen05 cta_group::2 */
+  HG_PATH_FUSED_PAIR = 3,  /* conv_pair_tc.cu: c1 + c2 of a ResBlock pair in one launch (reported under c2's name) */
+  HG_PATH_NARROW = 4,      /* conv_narrow.cu: 8 / 16 channels */
+  HG_PATH_POST = 5,        /* tail.cu: conv_post + tanh (+ int16) */
+  HG_PATH_REPACK = 6       /* tail.cu: mel -> operand layout */
+};
 HG_API int hg_layer_count(const HgPlan* plan, int* count);
+/* Static description of plan layer `index`; the tiling fields are the single-CTA tcgen05 kernel's
+ * default choice — the launch-time choice (CTA-pair kernel, fused pair, epilogue slots) is what
+ * hg_profile_launch_info reports. */
 HG_API int hg_layer_info(const HgPlan* plan, int index, int precision, HgLayerInfo* info);
+/* Launch `launch` (0-based) of this thread's last hg_profile_forward: which kernel family ran and with
+ * which tiling. */
+HG_API int hg_profile_launch_info(const HgPlan* plan, int launch, HgLayerInfo* info);
 HG_API int hg_profile_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC, int64_t sT, int B,
                               int T, void* out, int out_dtype, float out_scale, int precision,
                               void* workspace, size_t workspace_bytes, void* stream,

@@ -238,6 +238,21 @@ def test_vocoder_infer_drop_in():
         assert np.array_equal(w, wavs[i][:n])  # bit-identical to the padded run
 
 
+def test_profile_reports_what_each_launch_ran():
+    m = make_generator(fx.V1, precision="bf16").cuda()
+    mel = fx.synthetic_mel(2, 64, seed=5).cuda()
+    rows = m.profile_layers(mel)
+    assert len(rows) == m.kernel_launches(2, 64) == 61
+    assert all(r["ms"] > 0 for r in rows)
+    by_name = {r["name"]: r for r in rows}
+    assert by_name["mel_to_operand"]["kernel"] == "repack" and by_name["conv_post"]["kernel"] == "conv_post"
+    assert by_name["resblocks.2.convs1.0"]["kernel"] == "tcgen05 cta_group::2"      # 256 ch, k = 11
+    assert by_name["resblocks.3.convs1.0"]["kernel"] == "tcgen05"                   # 128 ch, k = 3: resident weights
+    assert by_name["resblocks.8.convs2.1"]["kernel"] == "tcgen05 fused pair" and "resblocks.8.convs1.1" not in by_name
+    m.precision = "fp32_ffma"
+    assert {r["kernel"] for r in m.profile_layers(mel)} == {"repack", "cuda-core", "conv_post"}
+
+
 def test_full_size_cross_check_against_ffma():
     """BASELINE cfg-2 scale (16 x 800 frames): the tensor-core fp32 path against the exact-fp32
     CUDA-core path on the device (the CPU oracle would take minutes), plus bf16 SNR."""

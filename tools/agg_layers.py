@@ -19,6 +19,6 @@ for r in rows:
     a=agg.setdefault(st,[0,0,0,r]); a[0]+=r["ms"]; a[1]+=fl; a[2]+=1
 stage={}
 for k,(ms,fl,n,r) in agg.items():
-    print(f"{k:20s} n={n} {ms:7.3f} ms  {fl/ms/1e9:8.1f} TFLOP/s  ms={r.get('m_subtiles')} st={r.get('stages')} res={r.get('weights_resident')} nb={r.get('slab_buffers')} smem={r.get('smem_bytes')}")
+    print(f"{k:20s} n={n} {ms:7.3f} ms  {fl/ms/1e9:8.1f} TFLOP/s  {r.get('kernel','')} ms={r.get('m_subtiles')} st={r.get('stages')} res={r.get('weights_resident')} nb={r.get('slab_buffers')} smem={r.get('smem_bytes')}")
     s=k.split()[0]; stage[s]=stage.get(s,0)+ms
 print({k:round(v,2) for k,v in stage.items()})

@@ -55,8 +55,8 @@ for r in rows:
                     by += e * (4 if j > 0 else 0)     # xs in
                     by += e * (4 if (j < 2 or i == 3) else 2)  # xs / x out, or next-stage operand out
         shape = f"{cin}->{cout} k{k}" + (f" d{r['dilation']}" if r["kind"] == 0 else f" s{r['stride']}")
-        path = "conv_pair_tc (fused pair)" if (".convs2." in n and n.replace(".convs2.", ".convs1.") not in names) else (
-            "tcgen05" if r.get("tensor_core") else "cuda-core")
+        path = r.get("kernel") or ("conv_pair_tc (fused pair)" if (".convs2." in n and n.replace(".convs2.", ".convs1.") not in names) else (
+            "tcgen05" if r.get("tensor_core") else "cuda-core"))
     t_f, t_b = fl / TF * 1e3, by / BW * 1e3
     roof = max(t_f, t_b)
     tot_ms += r["ms"]; tot_roof += roof

@@ -35,7 +35,11 @@ class HgConfig(ctypes.Structure):
 class HgLayerInfo(ctypes.Structure):
     _fields_ = [("name", ctypes.c_char * 64)] + [(n, ctypes.c_int32) for n in (
         "kind", "c_in", "c_out", "k", "dilation", "stride", "tensor_core", "n_tile", "k_chunk", "m_subtiles",
-        "stages", "smem_bytes", "weights_resident", "slab_buffers")]
+        "stages", "smem_bytes", "weights_resident", "slab_buffers", "kernel_path")]
+
+
+KERNEL_PATHS = {0: "cuda-core", 1: "tcgen05", 2: "tcgen05 cta_group::2", 3: "tcgen05 fused pair", 4: "cuda-core narrow",
+                5: "conv_post", 6: "repack"}
 
 
 class HgStackLayer(ctypes.Structure):
@@ -88,13 +92,14 @@ def lib() -> ctypes.CDLL:
     L.hg_op_conv_pair.argtypes = [i, vp, i, i, i, i, i, vp, vp, vp, vp, f, vp, vp, vp]
     L.hg_layer_count.argtypes = [vp, ctypes.POINTER(i)]
     L.hg_layer_info.argtypes = [vp, i, i, ctypes.POINTER(HgLayerInfo)]
+    L.hg_profile_launch_info.argtypes = [vp, i, ctypes.POINTER(HgLayerInfo)]
     L.hg_profile_forward.argtypes = [vp, vp, i64, i64, i64, i, i, vp, i, f, i, vp, sz, vp, ctypes.POINTER(i),
                                      ctypes.POINTER(f), i, ctypes.POINTER(i)]
     for name in ("hg_plan_create", "hg_plan_upload_weight", "hg_plan_finalize", "hg_workspace_bytes",
                  "hg_forward_launches", "hg_forward", "hg_halo_frames", "hg_forward_ragged", "hg_stack_create",
                  "hg_stack_workspace_bytes", "hg_stack_forward", "hg_plan_destroy", "hg_op_conv1d",
                  "hg_op_conv_transpose1d", "hg_op_conv_post", "hg_op_conv_pair", "hg_selftest_tcgen05", "hg_layer_count",
-                 "hg_layer_info",
+                 "hg_layer_info", "hg_profile_launch_info",
                  "hg_profile_forward"):
         getattr(L, name).restype = i
     if L.hg_abi_version() != 1:

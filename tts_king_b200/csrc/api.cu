@@ -437,19 +437,32 @@ extern "C" int hg_plan_destroy(HgPlan* plan) {
 
 // ------------------------------------------------------------------------------------------------
 // optional per-launch event recording (hg_profile_forward)
+// what a launch actually ran (kernel family + tiling), reported through hg_profile_launch_info
+struct LaunchRec {
+  int path = HG_PATH_CUDA_CORE, n_tile = 0, kc = 0, ms = 0, stages = 0, nbuf = 0, resident = 0;
+  size_t smem = 0;
+};
 struct ProfSink {
   cudaStream_t st;
   std::vector<cudaEvent_t> ev;   // ev[0] = before the first launch, ev[i+1] = after launch i
   std::vector<int> layer;        // plan layer index per launch (-1 = mel repack)
+  std::vector<LaunchRec> rec;
 };
 static thread_local ProfSink* g_prof = nullptr;
-static void prof_mark(int layer_index) {
+static thread_local std::vector<std::pair<int, LaunchRec>> g_last_profile;  // (layer, record) of the last hg_profile_forward
+static void prof_mark(int layer_index, const LaunchRec& rec = LaunchRec()) {
   if (!g_prof) return;
   cudaEvent_t e;
   if (cudaEventCreate(&e) != cudaSuccess) return;
   cudaEventRecord(e, g_prof->st);
   g_prof->ev.push_back(e);
-  if (layer_index > -2) g_prof->layer.push_back(layer_index);
+  if (layer_index > -2) { g_prof->layer.push_back(layer_index); g_prof->rec.push_back(rec); }
+}
+static LaunchRec make_rec(int path, int n_tile = 0, int kc = 0, int ms = 0, int stages = 0, int nbuf = 0, bool resident = false,
+                          size_t smem = 0) {
+  LaunchRec r;
+  r.path = path; r.n_tile = n_tile; r.kc = kc; r.ms = ms; r.stages = stages; r.nbuf = nbuf; r.resident = resident ? 1 : 0; r.smem = smem;
+  return r;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -625,7 +638,7 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
         const size_t smem = conv_tc2_smem_bytes(l.n_tile, slab_rows, nbuf, stages, slot);
         cudaError_t e = launch_conv_tc2(l.n_tile, ms, maps, p, smem, 2 * pairs, st);
         if (e != cudaSuccess) return fail(HG_ECUDA, "conv_tc2 launch (%s): %s", l.name.c_str(), cudaGetErrorString(e));
-        if (g_prof) prof_mark(static_cast<int>(&l - plan->layers.data()));
+        if (g_prof) prof_mark(static_cast<int>(&l - plan->layers.data()), make_rec(HG_PATH_TC_CTA_PAIR, l.n_tile, 64, ms, stages, nbuf, false, smem));
         return HG_OK;
       }
     }
@@ -686,7 +699,7 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
                 l.name.c_str(), grid, n / grid, tot / grid, a / grid, 100 * a / tot, sl / grid, 100 * sl / tot, w / grid, 100 * w / tot);
       }
       if (e != cudaSuccess) return fail(HG_ECUDA, "conv_tc launch (%s): %s", l.name.c_str(), cudaGetErrorString(e));
-      if (g_prof) prof_mark(static_cast<int>(&l - plan->layers.data()));
+      if (g_prof) prof_mark(static_cast<int>(&l - plan->layers.data()), make_rec(HG_PATH_TC, l.n_tile, l.kc, t.ms, t.stages, t.nbuf, t.resident, t.smem));
       return HG_OK;
     }
   }
@@ -699,7 +712,7 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
     np.w = l.w_ffma; np.epi = epi;
     cudaError_t e = launch_conv_narrow(l.cin, np, st, rag);
     if (e != cudaSuccess) return fail(HG_ECUDA, "conv_narrow launch (%s): %s", l.name.c_str(), cudaGetErrorString(e));
-    if (g_prof) prof_mark(static_cast<int>(&l - plan->layers.data()));
+    if (g_prof) prof_mark(static_cast<int>(&l - plan->layers.data()), make_rec(HG_PATH_NARROW));
     return HG_OK;
   }
   FfmaConvParams f;
@@ -711,7 +724,7 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
   f.w = l.w_ffma; f.epi = epi;
   cudaError_t e = launch_conv_ffma(f, st, rag);
   if (e != cudaSuccess) return fail(HG_ECUDA, "conv_ffma launch (%s): %s", l.name.c_str(), cudaGetErrorString(e));
-  if (g_prof) prof_mark(static_cast<int>(&l - plan->layers.data()));
+  if (g_prof) prof_mark(static_cast<int>(&l - plan->layers.data()), make_rec(HG_PATH_CUDA_CORE));
   return HG_OK;
 }
 
@@ -817,7 +830,7 @@ static int run_pair(HgPlan* plan, const Layer& l1, const Layer& l2, const PairTi
             s[11], s[12], s[13], s[14]);
   }
   if (e != cudaSuccess) return fail(HG_ECUDA, "conv_pair_tc launch (%s): %s", l2.name.c_str(), cudaGetErrorString(e));
-  if (g_prof) prof_mark(static_cast<int>(&l2 - plan->layers.data()));
+  if (g_prof) prof_mark(static_cast<int>(&l2 - plan->layers.data()), make_rec(HG_PATH_FUSED_PAIR, c, c, t.ms, t.stages, 2, t.resident, t.smem));
   return HG_OK;
 }
 
@@ -935,7 +948,7 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
   cudaError_t e = launch_mel_to_operand(mel, sB, sC, sT, B, c.num_mels, T, mel_pitch(plan, precision), fmt, ws.mel.a0,
                                         ws.mel.a1, st);
   if (e != cudaSuccess) return fail(HG_ECUDA, "mel_to_operand: %s", cudaGetErrorString(e));
-  prof_mark(-1);
+  prof_mark(-1, make_rec(HG_PATH_REPACK));
 
   // x = conv_pre(x)  :186 ; only leaky_relu(x) is consumed (by ups[0], :188-189)
   int a_cur = 1;  // operand buffer holding leaky_relu(current x)
@@ -1019,7 +1032,7 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
                        post.w_post_host.empty() ? nullptr : post.w_post_host.data(),
                        ragged_items(&rag_store, B, L, 0, /*with_halo=*/false));  // the last layer feeds nobody
   if (e != cudaSuccess) return fail(HG_ECUDA, "conv_post: %s", cudaGetErrorString(e));
-  prof_mark(static_cast<int>(plan->layers.size()) - 1);
+  prof_mark(static_cast<int>(plan->layers.size()) - 1, make_rec(HG_PATH_POST));
   return HG_OK;
 }
 
@@ -1208,6 +1221,8 @@ extern "C" int hg_profile_forward(HgPlan* plan, const float* mel, int64_t sB, in
   g_prof = nullptr;
   cudaError_t es = cudaStreamSynchronize(sink.st);
   int n = 0;
+  g_last_profile.clear();
+  for (size_t i = 0; i < sink.layer.size() && i < sink.rec.size(); ++i) g_last_profile.emplace_back(sink.layer[i], sink.rec[i]);
   if (!rc && es == cudaSuccess) {
     n = static_cast<int>(sink.layer.size());
     if (n > max_launches) n = max_launches;
@@ -1222,6 +1237,28 @@ extern "C" int hg_profile_forward(HgPlan* plan, const float* mel, int64_t sB, in
   if (rc) return rc;
   if (es != cudaSuccess) return fail(HG_ECUDA, "profile_forward: %s", cudaGetErrorString(es));
   *n_launches = n;
+  return HG_OK;
+}
+
+extern "C" int hg_profile_launch_info(const HgPlan* plan, int launch, HgLayerInfo* info) {
+  if (!plan || !info) return fail(HG_EINVAL, "null argument");
+  if (launch < 0 || launch >= static_cast<int>(g_last_profile.size()))
+    return fail(HG_EINVAL, "launch %d outside the last hg_profile_forward of this thread (%zu launches)", launch, g_last_profile.size());
+  const int li = g_last_profile[launch].first;
+  const LaunchRec& r = g_last_profile[launch].second;
+  memset(info, 0, sizeof(*info));
+  if (li >= 0 && li < static_cast<int>(plan->layers.size())) {
+    const Layer& l = plan->layers[li];
+    snprintf(info->name, sizeof(info->name), "%s", l.name.c_str());
+    info->kind = l.kind; info->c_in = l.cin; info->c_out = l.cout; info->k = l.k; info->dilation = l.dil; info->stride = l.stride;
+  } else {
+    snprintf(info->name, sizeof(info->name), "mel_to_operand");
+    info->kind = -1;
+  }
+  info->kernel_path = r.path;
+  info->tensor_core = (r.path == HG_PATH_TC || r.path == HG_PATH_TC_CTA_PAIR || r.path == HG_PATH_FUSED_PAIR) ? 1 : 0;
+  info->n_tile = r.n_tile; info->k_chunk = r.kc; info->m_subtiles = r.ms; info->stages = r.stages;
+  info->smem_bytes = static_cast<int32_t>(r.smem); info->weights_resident = r.resident; info->slab_buffers = r.nbuf;
   return HG_OK;
 }
 

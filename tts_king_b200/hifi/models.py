@@ -205,6 +205,12 @@ class _Engine:
                                                     ctypes.byref(n)))
         return [(idx[i], ms[i]) for i in range(n.value)]
 
+    def launch_info(self, launch: int) -> _native.HgLayerInfo:
+        """Kernel family and tiling launch `launch` of this thread's last profile() actually used."""
+        info = _native.HgLayerInfo()
+        _native.check(self.L.hg_profile_launch_info(self.plan, launch, ctypes.byref(info)))
+        return info
+
 
 class Generator(nn.Module):
     """``Generator(h)`` — reference hifi/models.py:146-210.
@@ -333,17 +339,17 @@ class Generator(nn.Module):
         x = x.detach().float()
         B, _, T = x.shape
         out = torch.empty((B, 1, T * self.hop_length), device=x.device, dtype=torch.float32)
-        table = eng.layer_table(prec)
         rows = []
-        for li, ms in eng.profile(x, out, prec):
+        for i, (li, ms) in enumerate(eng.profile(x, out, prec)):
+            t = eng.launch_info(i)  # what the launch actually ran (kernel family, tiling)
             if li < 0:
-                rows.append(dict(name="mel_to_operand", kind=-1, ms=ms))
+                rows.append(dict(name="mel_to_operand", kind=-1, kernel=_native.KERNEL_PATHS[t.kernel_path], ms=ms))
                 continue
-            t = table[li]
             rows.append(dict(name=t.name.decode(), kind=t.kind, c_in=t.c_in, c_out=t.c_out, k=t.k, dilation=t.dilation,
-                             stride=t.stride, tensor_core=bool(t.tensor_core), n_tile=t.n_tile, k_chunk=t.k_chunk,
-                             m_subtiles=t.m_subtiles, stages=t.stages, smem_bytes=t.smem_bytes,
-                             weights_resident=bool(t.weights_resident), slab_buffers=t.slab_buffers, ms=ms))
+                             stride=t.stride, kernel=_native.KERNEL_PATHS[t.kernel_path], tensor_core=bool(t.tensor_core),
+                             n_tile=t.n_tile, k_chunk=t.k_chunk, m_subtiles=t.m_subtiles, stages=t.stages,
+                             smem_bytes=t.smem_bytes, weights_resident=bool(t.weights_resident),
+                             slab_buffers=t.slab_buffers, ms=ms))
         return rows
 
     # ------------------------------------------------------------------ internals
