@@ -247,6 +247,21 @@ static Layer make_convT(const std::string& name, int cin, int cout, int k, int s
   return l;
 }
 
+// device properties + the bring-up switches (HG_* environment variables)
+static void init_plan_env(HgPlan* p, int device) {
+  p->device = device;
+  cudaDeviceProp pr;
+  if (cudaGetDeviceProperties(&pr, device) == cudaSuccess) p->sm_count = pr.multiProcessorCount;
+  p->desc_mode = env_int("HG_DESC_MODE", 0);
+  p->force_ms = env_int("HG_TC_MS", 0);
+  p->force_stages = env_int("HG_TC_STAGES", 0);
+  p->force_ffma = env_int("HG_FORCE_FFMA", 0) != 0;
+  p->ctas_per_sm = env_int("HG_TC_CTAS_PER_SM", 1);
+  p->fuse_pairs = env_int("HG_FUSE_PAIRS", 1) != 0;
+  p->epi_tma = env_int("HG_EPI_TMA", 1) != 0;
+  p->use_tc2 = env_int("HG_TC2", 1) != 0;
+}
+
 static int rb_dilations(const HgConfig& c) { return c.resblock_type == 1 ? 3 : 2; }
 
 extern "C" int hg_plan_create(const HgConfig* cfg, int device, HgPlan** out) {
@@ -262,17 +277,7 @@ extern "C" int hg_plan_create(const HgConfig* cfg, int device, HgPlan** out) {
   if (rc) return rc;
   HgPlan* p = new HgPlan();
   p->cfg = *cfg;
-  p->device = device;
-  cudaDeviceProp pr;
-  if (cudaGetDeviceProperties(&pr, device) == cudaSuccess) p->sm_count = pr.multiProcessorCount;
-  p->desc_mode = env_int("HG_DESC_MODE", 0);
-  p->force_ms = env_int("HG_TC_MS", 0);
-  p->force_stages = env_int("HG_TC_STAGES", 0);
-  p->force_ffma = env_int("HG_FORCE_FFMA", 0) != 0;
-  p->ctas_per_sm = env_int("HG_TC_CTAS_PER_SM", 1);
-  p->fuse_pairs = env_int("HG_FUSE_PAIRS", 1) != 0;
-  p->epi_tma = env_int("HG_EPI_TMA", 1) != 0;
-  p->use_tc2 = env_int("HG_TC2", 1) != 0;
+  init_plan_env(p, device);
   const int uic = cfg->upsample_initial_channel;
   p->layers.push_back(make_conv("conv_pre", cfg->num_mels, uic, 7, 1));
   for (int i = 0; i < cfg->num_upsamples; ++i) {
@@ -1060,19 +1065,6 @@ extern "C" int hg_forward_ragged(HgPlan* plan, const float* mel, int64_t sB, int
 // ------------------------------------------------------------------------------------------------
 // conv stacks: FastSpeech2's PostNet (fs_two/transformer/Layers.py:71-143, BatchNorm folded by the
 // caller) and mel_linear (fs_two/model/fastspeech2.py:101-104) on the generator's conv kernels
-static void init_plan_env(HgPlan* p, int device) {
-  p->device = device;
-  cudaDeviceProp pr;
-  if (cudaGetDeviceProperties(&pr, device) == cudaSuccess) p->sm_count = pr.multiProcessorCount;
-  p->desc_mode = env_int("HG_DESC_MODE", 0);
-  p->force_ms = env_int("HG_TC_MS", 0);
-  p->force_stages = env_int("HG_TC_STAGES", 0);
-  p->force_ffma = env_int("HG_FORCE_FFMA", 0) != 0;
-  p->ctas_per_sm = env_int("HG_TC_CTAS_PER_SM", 1);
-  p->fuse_pairs = env_int("HG_FUSE_PAIRS", 1) != 0;
-  p->epi_tma = env_int("HG_EPI_TMA", 1) != 0;
-  p->use_tc2 = env_int("HG_TC2", 1) != 0;
-}
 
 extern "C" int hg_stack_create(const HgStackLayer* layers, int n_layers, int device, HgPlan** out) {
   if (!layers || !out) return fail(HG_EINVAL, "null argument");
