@@ -158,6 +158,34 @@ HG_API int hg_stack_forward(HgPlan* plan, const float* x, int64_t sB, int64_t sC
                      size_t workspace_bytes, void* stream);
 
 /*
+ * hg_forward whose last layer writes only the samples [skip_samples, skip_samples + keep_samples) of
+ * every item, at out[b * out_item_stride + (t - skip_samples)] — the "compute, then gather" of
+ * time-chunked long-form synthesis as one step: a chunk computed with halo
+ * frames drops its halo samples in conv_post's epilogue and stores its owned samples directly at
+ * their place in the final waveform.  `out` may be a peer-mapped address of a buffer on ANOTHER GPU
+ * of the node (CUDA IPC + hg_enable_peer_access): the stores then travel over NVLink / NVSwitch and
+ * no separate gather collective runs.
+ */
+HG_API int hg_forward_window(HgPlan* plan, const float* mel, int64_t sB, int64_t sC, int64_t sT, int B, int T,
+                      void* out, int64_t out_item_stride, int64_t skip_samples, int64_t keep_samples,
+                      int out_dtype, float out_scale, int precision, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/*
+ * CUDA IPC for the direct-store gather: the owner of the final waveform buffer exports it
+ * (hg_ipc_export: 64-byte handle of the underlying allocation + the byte offset of `device_ptr` in it),
+ * the handle travels to the other ranks' processes by any means (the Python layer uses the process
+ * group), and each of them maps it FOR ITS OWN GPU (hg_ipc_import(device, ...) -> `ptr`, usable as
+ * `out` of hg_forward_window on `device`; `base` is what hg_ipc_close takes).  Single node.
+ */
+HG_API int hg_ipc_export(const void* device_ptr, unsigned char* handle64, int64_t* offset);
+HG_API int hg_ipc_import(int device, const unsigned char* handle64, int64_t offset, void** base, void** ptr);
+HG_API int hg_ipc_close(int device, void* base);
+
+/* cudaDeviceEnablePeerAccess(device -> peer_device), idempotent; HG_ENODEVICE when there is no peer path. */
+HG_API int hg_enable_peer_access(int device, int peer_device);
+
+/*
  * Mel frames of right context a sample needs (13 for V1): the generator's
  * receptive reach, rounded up to frames.  What hg_forward_ragged adds to every item's length.
  */

@@ -238,6 +238,31 @@ def test_vocoder_infer_drop_in():
         assert np.array_equal(w, wavs[i][:n])  # bit-identical to the padded run
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_forward_into_writes_only_the_window(prec):
+    """hg_forward_window: the last kernel stores the owned samples of a haloed chunk in place."""
+    m = make_generator(fx.V1, precision=prec).cuda()
+    mel = fx.synthetic_mel(2, 50, seed=13).cuda()
+    with torch.no_grad():
+        full = m(mel)
+        full16 = m.generate_int16(mel)
+        big = torch.full((2, 1, 40 * 256 + 77), 7.0, device="cuda")          # a window of a larger buffer
+        m.forward_into(mel, big[:, :, 11:11 + 30 * 256], skip_frames=9, keep_frames=30)
+        assert torch.equal(big[:, :, 11:11 + 30 * 256], full[:, :, 9 * 256:39 * 256])
+        assert (big[:, :, :11] == 7.0).all() and (big[:, :, 11 + 30 * 256:] == 7.0).all()  # nothing outside it
+        o16 = torch.zeros((2, 1, 50 * 256), dtype=torch.int16, device="cuda")
+        m.forward_into(mel, o16)
+        assert torch.equal(o16, full16)
+        # chunked long-form without the concatenation
+        out = torch.empty_like(full)
+        parallel.chunked_forward_into(m, mel, 17, parallel.halo_frames(m.h), out)
+        assert torch.equal(out, full)
+    with pytest.raises(ValueError):
+        m.forward_into(mel, torch.empty((2, 1, 10 * 256), device="cuda"), skip_frames=45, keep_frames=10)
+    with pytest.raises(ValueError):
+        m.forward_into(mel, torch.empty((2, 1, 10 * 256 + 1), device="cuda"), skip_frames=0, keep_frames=10)
+
+
 def test_profile_reports_what_each_launch_ran():
     m = make_generator(fx.V1, precision="bf16").cuda()
     mel = fx.synthetic_mel(2, 64, seed=5).cuda()
@@ -314,6 +339,7 @@ def test_multi_gpu_sharding_matches_single_gpu():
     for prec in ("fp32", "bf16"):
         assert res[prec]["utterance_sharding_bitwise_equal"]
         assert res[prec]["long_form_max_abs_vs_single_gpu"] <= 1e-6
+        assert res[prec]["direct_p2p_store_bitwise_equal"]  # gather fused into conv_post's stores (NVLink P2P)
 
 
 @pytest.mark.parametrize("env", [{"HG_TC2": "0"}, {"HG_FUSE_PAIRS": "0"}, {"HG_EPI_TMA": "0"},

@@ -132,6 +132,34 @@ def test_chunked_forward_equals_full_forward():
     assert max_abs(y_bad.numpy(), full.numpy()) > 1e-9
 
 
+def test_direct_store_chunking_index_algebra(monkeypatch):
+    """chunked_forward_into / sharded_long_form_into: every chunk's window lands at its place in the final
+    buffer (the oracle stands in for Generator.forward_into; ranks are emulated one after the other)."""
+    cfg = fx.TINY_RB1
+    sd = {k: v.double() for k, v in stored_state(golden("tiny_rb1"), "alive.").items()}
+
+    class Gen:
+        h = fx.make_h(cfg)
+        hop_length = 256
+
+        def forward_into(self, x, out, skip, keep, max_wav_value=None):
+            out.copy_(torch_oracle.forward(cfg, sd, x)[:, :, skip * 256:(skip + keep) * 256])
+            return out
+
+    T = 70
+    mel = fx.synthetic_mel(1, T, seed=3).double()
+    full = torch_oracle.forward(cfg, sd, mel)
+    out = torch.zeros_like(full)
+    parallel.chunked_forward_into(Gen(), mel, 23, 13, out)
+    assert max_abs(out.numpy(), full.numpy()) <= 1e-13
+    out = torch.zeros_like(full)
+    for a, b in ((0, 25), (25, 48), (48, 70)):
+        lo, hi = max(0, a - 13), min(T, b + 13)
+        monkeypatch.setattr(parallel, "exchange_halo", lambda local, halo, group=None, lo=lo, hi=hi, a=a, b=b: (mel[:, :, lo:hi], a - lo, hi - b))
+        parallel.sharded_long_form_into(Gen(), mel[:, :, a:b], 13, out, a, chunk_frames=9)
+    assert max_abs(out.numpy(), full.numpy()) <= 1e-13
+
+
 # ------------------------------------------------------------------ ragged batches (N2)
 def test_length_buckets_partition_and_cost():
     from tts_king_b200 import ragged

@@ -7,7 +7,9 @@
 1. utterance sharding: a ragged set of utterances split across ranks (greedy longest-first) must
    reproduce, bit for bit, what one GPU computes for the same utterances;
 2. one long mel time-sharded across ranks: 13-frame halo exchange over NCCL + gather must equal the
-   single-GPU forward of the whole mel.
+   single-GPU forward of the whole mel;
+3. the same with the gather fused into the last kernel (every rank stores its samples straight into
+   rank 0's buffer through a peer mapping, over NVLink): bit-identical, float and int16.
 Rank 0 prints one JSON line.
 """
 import json
@@ -53,6 +55,15 @@ def main():
         with torch.no_grad():
             wav_local = parallel.sharded_long_form(m, local_mel, halo, hop)
         wav = parallel.gather_wav(wav_local, dst=0)
+        # ---- 3. the same, with the gather fused into the last kernel: every rank's conv_post stores its samples
+        # straight into rank 0's buffer over NVLink (CUDA IPC peer mapping), int16 tail included
+        direct = parallel.share_output_buffer((1, 1, T * hop), torch.float32, owner=0)
+        direct16 = parallel.share_output_buffer((1, 1, T * hop), torch.int16, owner=0)
+        with torch.no_grad():
+            parallel.sharded_long_form_into(m, local_mel, halo, direct, chunks[rank].start, chunk_frames=29)
+            parallel.sharded_long_form_into(m, local_mel, halo, direct16, chunks[rank].start, chunk_frames=64)
+        torch.cuda.synchronize()
+        dist.barrier()
         if rank == 0:
             merged = {}
             for d in gathered:
@@ -62,8 +73,10 @@ def main():
                     np.array_equal(merged[i], m(fx.synthetic_mel(1, lengths[i], seed=100 + i).to(dev)).cpu().numpy())
                     for i in merged)
                 full = m(mel.to(dev))
+                full16 = m.generate_int16(mel.to(dev))
             err = float((wav - full).abs().max())
-            out[prec] = {"utterance_sharding_bitwise_equal": bool(ok), "n_utterances": len(lengths),
+            out[prec] = {"direct_p2p_store_bitwise_equal": bool(torch.equal(direct, full)) and bool(torch.equal(direct16, full16)),
+                         "direct_buffer_device_on_this_rank": str(direct.device),"utterance_sharding_bitwise_equal": bool(ok), "n_utterances": len(lengths),
                          "long_form_frames": T, "long_form_max_abs_vs_single_gpu": err,
                          "halo_frames": halo, "halo_bytes_per_side": halo * 80 * 4}
         dist.barrier()

@@ -126,6 +126,24 @@ def main():
                               "audio_s": audio_s, "audio_sec_per_sec": audio_s / (ms * 1e-3), "frames": T,
                               "frames_per_rank": c.frames, "halo_frames": halo, "halo_bytes_per_side": halo * 80 * 4,
                               "wav_samples_gathered": int(wav.shape[-1]), "includes": "halo exchange + forward + gather to rank 0"}))
+        # the same with the gather fused into the last kernel: every rank's conv_post stores its samples straight
+        # into rank 0's buffer through a peer mapping (NVLink), float32 like the NCCL variant and int16 (the
+        # HIFIapi.generate tail, half the bytes)
+        for dt, label in ((torch.float32, "f32"), (torch.int16, "i16")):
+            full = parallel.share_output_buffer((1, 1, T * hop), dt, owner=0)
+
+            def run_direct():
+                with torch.no_grad():
+                    parallel.sharded_long_form_into(m, local_mel, halo, full, c.start, chunk_frames=sub)
+
+            run_direct()
+            ms, _ = timed(run_direct, dev, world, reps=2)
+            if rank == 0:
+                print(json.dumps({"config": f"cfg5_60min_direct_p2p_store_{label}", "n_gpus": world, "precision": args.precision, "ms": ms,
+                                  "audio_s": audio_s, "audio_sec_per_sec": audio_s / (ms * 1e-3),
+                                  "includes": "halo exchange + forward with conv_post storing into rank 0's buffer over NVLink (no gather collective)"}))
+            dist.barrier()
+            del full
     dist.destroy_process_group()
 
 

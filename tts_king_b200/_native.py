@@ -79,6 +79,11 @@ def lib() -> ctypes.CDLL:
     L.hg_workspace_bytes.argtypes = [vp, i, i, i, ctypes.POINTER(sz)]
     L.hg_forward_launches.argtypes = [vp, i, i, i, ctypes.POINTER(i)]
     L.hg_forward.argtypes = [vp, vp, i64, i64, i64, i, i, vp, i, f, i, vp, sz, vp]
+    L.hg_forward_window.argtypes = [vp, vp, i64, i64, i64, i, i, vp, i64, i64, i64, i, f, i, vp, sz, vp]
+    L.hg_enable_peer_access.argtypes = [i, i]
+    L.hg_ipc_export.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(i64)]
+    L.hg_ipc_import.argtypes = [i, ctypes.c_char_p, i64, ctypes.POINTER(vp), ctypes.POINTER(vp)]
+    L.hg_ipc_close.argtypes = [i, vp]
     L.hg_halo_frames.argtypes = [vp, ctypes.POINTER(i)]
     L.hg_forward_ragged.argtypes = [vp, vp, i64, i64, i64, i, i, ctypes.POINTER(ctypes.c_int32), vp, i, f, i, vp, sz, vp]
     L.hg_stack_create.argtypes = [ctypes.POINTER(HgStackLayer), i, i, ctypes.POINTER(vp)]
@@ -96,7 +101,7 @@ def lib() -> ctypes.CDLL:
     L.hg_profile_forward.argtypes = [vp, vp, i64, i64, i64, i, i, vp, i, f, i, vp, sz, vp, ctypes.POINTER(i),
                                      ctypes.POINTER(f), i, ctypes.POINTER(i)]
     for name in ("hg_plan_create", "hg_plan_upload_weight", "hg_plan_finalize", "hg_workspace_bytes",
-                 "hg_forward_launches", "hg_forward", "hg_halo_frames", "hg_forward_ragged", "hg_stack_create",
+                 "hg_forward_launches", "hg_forward", "hg_halo_frames", "hg_forward_ragged", "hg_forward_window", "hg_enable_peer_access", "hg_ipc_export", "hg_ipc_import", "hg_ipc_close", "hg_stack_create",
                  "hg_stack_workspace_bytes", "hg_stack_forward", "hg_plan_destroy", "hg_op_conv1d",
                  "hg_op_conv_transpose1d", "hg_op_conv_post", "hg_op_conv_pair", "hg_selftest_tcgen05", "hg_layer_count",
                  "hg_layer_info", "hg_profile_launch_info",

@@ -21,7 +21,7 @@ cudaError_t launch_conv_tc(int n_t, int kc, int ms, bool split, const CUtensorMa
 cudaError_t launch_conv_ffma(FfmaConvParams p, cudaStream_t st, const RaggedItems* items = nullptr);
 cudaError_t launch_conv_post(const float* x, int B, int L, int C, const float* w_tapmajor, float bias, float* out_f32,
                              int16_t* out_i16, float out_scale, cudaStream_t st, const float* w_host_tapmajor,
-                             const RaggedItems* items = nullptr);
+                             const RaggedItems* items = nullptr, long long item_stride = 0, int skip = 0, int keep = 0);
 cudaError_t launch_mel_to_operand(const float* mel, long long sB, long long sC, long long sT, int B, int C, int T,
                                   int c_pad, int a_fmt, void* a0, void* a1, cudaStream_t st, int act = 0, float slope = 1.f);
 cudaError_t launch_f32_to_operand(const float* x, long long n, float slope, int a_fmt, void* a0, void* a1,
@@ -479,6 +479,13 @@ struct RaggedCtx {
   int T;
 };
 static thread_local const RaggedCtx* g_rag = nullptr;
+
+// output window of the last layer (hg_forward_window)
+struct WindowCtx {
+  long long item_stride;
+  int skip, keep;
+};
+static thread_local const WindowCtx* g_win = nullptr;
 
 // valid GEMM rows per item for a launch whose input has L_in rows per item (rows = L_in + extra)
 static const RaggedItems* ragged_items(RaggedItems* store, int B, int L_in, int extra, bool with_halo = true) {
@@ -1035,9 +1042,96 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
                        out_dtype == HG_OUT_F32 ? static_cast<float*>(out) : nullptr,
                        out_dtype == HG_OUT_I16 ? static_cast<int16_t*>(out) : nullptr, out_scale, st,
                        post.w_post_host.empty() ? nullptr : post.w_post_host.data(),
-                       ragged_items(&rag_store, B, L, 0, /*with_halo=*/false));  // the last layer feeds nobody
+                       ragged_items(&rag_store, B, L, 0, /*with_halo=*/false),  // the last layer feeds nobody
+                       g_win ? g_win->item_stride : 0, g_win ? g_win->skip : 0, g_win ? g_win->keep : 0);
   if (e != cudaSuccess) return fail(HG_ECUDA, "conv_post: %s", cudaGetErrorString(e));
   prof_mark(static_cast<int>(plan->layers.size()) - 1, make_rec(HG_PATH_POST));
+  return HG_OK;
+}
+
+extern "C" int hg_forward_window(HgPlan* plan, const float* mel, int64_t sB, int64_t sC, int64_t sT, int B, int T, void* out,
+                                 int64_t out_item_stride, int64_t skip_samples, int64_t keep_samples, int out_dtype,
+                                 float out_scale, int precision, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_fwd_args(plan, B, T, precision);
+  if (rc) return rc;
+  long long hop = 1;
+  for (int i = 0; i < plan->cfg.num_upsamples; ++i) hop *= plan->cfg.upsample_rates[i];
+  const long long n = static_cast<long long>(T) * hop;
+  if (skip_samples < 0 || keep_samples < 1 || skip_samples + keep_samples > n)
+    return fail(HG_EINVAL, "window [%lld, %lld) outside the %lld samples of the forward", static_cast<long long>(skip_samples),
+                static_cast<long long>(skip_samples + keep_samples), n);
+  if (out_item_stride < keep_samples) return fail(HG_EINVAL, "out_item_stride %lld < keep_samples %lld", static_cast<long long>(out_item_stride), static_cast<long long>(keep_samples));
+  WindowCtx ctx{out_item_stride, static_cast<int>(skip_samples), static_cast<int>(keep_samples)};
+  g_win = &ctx;
+  rc = hg_forward(plan, mel, sB, sC, sT, B, T, out, out_dtype, out_scale, precision, workspace, workspace_bytes, stream);
+  g_win = nullptr;
+  return rc;
+}
+
+extern "C" int hg_enable_peer_access(int device, int peer_device) {
+  int rc = check_device(device);
+  if (rc) return rc;
+  if (device == peer_device) return HG_OK;
+  int can = 0;
+  CUDA_TRY(cudaDeviceCanAccessPeer(&can, device, peer_device));
+  if (!can) return fail(HG_ENODEVICE, "device %d cannot access device %d's memory (no NVLink / PCIe peer path)", device, peer_device);
+  int prev = 0;
+  CUDA_TRY(cudaGetDevice(&prev));
+  CUDA_TRY(cudaSetDevice(device));
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+  cudaSetDevice(prev);
+  if (e != cudaSuccess) return fail(HG_ECUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", device, peer_device, cudaGetErrorString(e));
+  return HG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one buffer, every GPU of the node: CUDA IPC export / import for the direct-store gather
+extern "C" int hg_ipc_export(const void* device_ptr, unsigned char* handle64, int64_t* offset) {
+  if (!device_ptr || !handle64 || !offset) return fail(HG_EINVAL, "null argument");
+  typedef CUresult (*RangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+  static RangeFn range = nullptr;
+  if (!range) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q) != cudaSuccess || !p)
+      return fail(HG_ECUDA, "cuMemGetAddressRange entry point unavailable");
+    range = reinterpret_cast<RangeFn>(p);
+  }
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (range(&base, &size, reinterpret_cast<CUdeviceptr>(device_ptr)) != CUDA_SUCCESS)
+    return fail(HG_EINVAL, "not a device allocation");
+  cudaIpcMemHandle_t h;
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  CUDA_TRY(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base)));
+  memcpy(handle64, &h, 64);
+  *offset = static_cast<int64_t>(reinterpret_cast<CUdeviceptr>(device_ptr) - base);
+  return HG_OK;
+}
+
+extern "C" int hg_ipc_import(int device, const unsigned char* handle64, int64_t offset, void** base, void** ptr) {
+  if (!handle64 || !base || !ptr) return fail(HG_EINVAL, "null argument");
+  int rc = check_device(device);
+  if (rc) return rc;
+  // opened with `device` current: the mapping is made for THIS device's kernels, with peer access to
+  // the owner enabled lazily (a mapping opened under the owner's device is not reachable from here)
+  CUDA_TRY(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* b = nullptr;
+  CUDA_TRY(cudaIpcOpenMemHandle(&b, h, cudaIpcMemLazyEnablePeerAccess));
+  *base = b;
+  *ptr = static_cast<unsigned char*>(b) + offset;
+  return HG_OK;
+}
+
+extern "C" int hg_ipc_close(int device, void* base) {
+  if (!base) return HG_OK;
+  int rc = check_device(device);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaIpcCloseMemHandle(base));
   return HG_OK;
 }
 

@@ -16,6 +16,16 @@ namespace hg {
 constexpr int kPostTile = 256;  // output samples per block
 constexpr int kPostK = 7;
 
+// Where the waveform goes: sample t of item b lands at out[b * item_stride + (t - skip)] when
+// skip <= t < skip + keep, and nowhere otherwise.  The dense forward uses {L, 0, L}; a time chunk
+// computed with halo frames drops its halo samples here and writes its owned samples straight into
+// their place in the final buffer — which may live on another GPU (peer-mapped: the stores travel
+// over NVLink, hg_forward_window).
+struct PostWindow {
+  long long item_stride;
+  int skip, keep;
+};
+
 // x: fp32 [B][L][C] raw stage output.  Block = kPostTile consecutive samples of one item.  The
 // (tile + 6) x C window is staged in shared memory with coalesced float4 loads (leaky_relu applied
 // once per element), rows padded by 4 floats so that a quarter-warp's LDS.128 hit distinct banks.
@@ -24,7 +34,7 @@ __global__ void __launch_bounds__(kPostTile) conv_post_kernel(const float* __res
                                                               const float* __restrict__ w,  // [7][C] tap-major
                                                               float bias, int tiles_per_item, float* __restrict__ out_f32,
                                                               int16_t* __restrict__ out_i16, float out_scale,
-                                                              const RaggedPrefix rag) {
+                                                              const RaggedPrefix rag, const PostWindow win) {
   extern __shared__ float psm[];
   const int pitch = VEC4 ? C + 4 : C + 1;
   float* xs = psm;                                   // [kPostTile + 6][pitch]
@@ -32,6 +42,7 @@ __global__ void __launch_bounds__(kPostTile) conv_post_kernel(const float* __res
   int b, tile;
   decode_tile(rag, tiles_per_item, static_cast<int>(blockIdx.x), b, tile);
   const int t0 = tile * kPostTile;
+  if (t0 + kPostTile <= win.skip || t0 >= win.skip + win.keep) return;  // whole tile outside the window
   const float* xb = x + static_cast<long long>(b) * L * C;
   for (int e = threadIdx.x; e < kPostK * C; e += kPostTile) ws[e] = w[e];
   if (VEC4) {
@@ -55,7 +66,7 @@ __global__ void __launch_bounds__(kPostTile) conv_post_kernel(const float* __res
   }
   __syncthreads();
   const int t = t0 + threadIdx.x;
-  if (t >= L) return;
+  if (t >= L || t < win.skip || t >= win.skip + win.keep) return;
   float acc = bias;
 #pragma unroll
   for (int j = 0; j < kPostK; ++j) {
@@ -73,7 +84,7 @@ __global__ void __launch_bounds__(kPostTile) conv_post_kernel(const float* __res
     }
   }
   const float y = tanhf(acc);
-  const long long o = static_cast<long long>(b) * L + t;
+  const long long o = static_cast<long long>(b) * win.item_stride + (t - win.skip);
   if (out_f32) out_f32[o] = y;
   if (out_i16) {
     // numpy float32 -> int16: truncate toward zero to int32, keep the low 16 bits (+1.0 -> -32768)
@@ -94,13 +105,14 @@ struct PostW32 {
 __global__ void __launch_bounds__(kPostTile) conv_post32_kernel(const float* __restrict__ x, int L, const PostW32 W,
                                                                 float bias, int tiles_per_item, float* __restrict__ out_f32,
                                                                 int16_t* __restrict__ out_i16, float out_scale,
-                                                                const RaggedPrefix rag) {
+                                                                const RaggedPrefix rag, const PostWindow win) {
   constexpr int C = 32, ROWS = kPostTile + kPostK - 1, PITCH = C + 4, PP = 9;
   __shared__ __align__(16) float xs[ROWS * PITCH];
   __shared__ float ps[ROWS * PP];
   int b, tile;
   decode_tile(rag, tiles_per_item, static_cast<int>(blockIdx.x), b, tile);
   const int t0 = tile * kPostTile;
+  if (t0 + kPostTile <= win.skip || t0 >= win.skip + win.keep) return;  // whole tile outside the window
   const float* xb = x + static_cast<long long>(b) * L * C;
   // stage the window: all of a thread's loads are issued before the first is consumed (the rolled
   // loop had one 16-byte load in flight per thread and ran at 2 TB/s, latency-bound)
@@ -146,12 +158,12 @@ __global__ void __launch_bounds__(kPostTile) conv_post32_kernel(const float* __r
   }
   __syncthreads();
   const int t = t0 + threadIdx.x;
-  if (t >= L) return;
+  if (t >= L || t < win.skip || t >= win.skip + win.keep) return;
   float acc = bias;
 #pragma unroll
   for (int j = 0; j < kPostK; ++j) acc += ps[(threadIdx.x + j) * PP + j];
   const float y = tanhf(acc);
-  const long long o = static_cast<long long>(b) * L + t;
+  const long long o = static_cast<long long>(b) * win.item_stride + (t - win.skip);
   if (out_f32) out_f32[o] = y;
   if (out_i16) {
     const int v = __float2int_rz(y * out_scale);
@@ -161,15 +173,20 @@ __global__ void __launch_bounds__(kPostTile) conv_post32_kernel(const float* __r
 
 cudaError_t launch_conv_post(const float* x, int B, int L, int C, const float* w_tapmajor, float bias,
                              float* out_f32, int16_t* out_i16, float out_scale, cudaStream_t st,
-                             const float* w_host_tapmajor, const RaggedItems* items) {
+                             const float* w_host_tapmajor, const RaggedItems* items, long long item_stride, int skip,
+                             int keep) {
   const int tiles = (L + kPostTile - 1) / kPostTile;
+  PostWindow win;
+  win.item_stride = item_stride > 0 ? item_stride : L;
+  win.skip = skip;
+  win.keep = keep > 0 ? keep : L - skip;
   RaggedPrefix rag;
   const int total = ragged_fill(&rag, items, B, L, kPostTile);
   if (C == 32 && w_host_tapmajor) {
     PostW32 W;
     for (int j = 0; j < kPostK; ++j)
       for (int c = 0; c < 32; ++c) W.w[j][c] = w_host_tapmajor[j * 32 + c];
-    conv_post32_kernel<<<static_cast<unsigned>(total), kPostTile, 0, st>>>(x, L, W, bias, tiles, out_f32, out_i16, out_scale, rag);
+    conv_post32_kernel<<<static_cast<unsigned>(total), kPostTile, 0, st>>>(x, L, W, bias, tiles, out_f32, out_i16, out_scale, rag, win);
     return cudaGetLastError();
   }
   const bool vec = (C & 3) == 0;
@@ -179,11 +196,11 @@ cudaError_t launch_conv_post(const float* x, int B, int L, int C, const float* w
   if (vec) {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(conv_post_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    conv_post_kernel<true><<<grid, kPostTile, smem, st>>>(x, L, C, w_tapmajor, bias, tiles, out_f32, out_i16, out_scale, rag);
+    conv_post_kernel<true><<<grid, kPostTile, smem, st>>>(x, L, C, w_tapmajor, bias, tiles, out_f32, out_i16, out_scale, rag, win);
   } else {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(conv_post_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    conv_post_kernel<false><<<grid, kPostTile, smem, st>>>(x, L, C, w_tapmajor, bias, tiles, out_f32, out_i16, out_scale, rag);
+    conv_post_kernel<false><<<grid, kPostTile, smem, st>>>(x, L, C, w_tapmajor, bias, tiles, out_f32, out_i16, out_scale, rag, win);
   }
   return cudaGetLastError();
 }

@@ -173,6 +173,20 @@ class _Engine:
                 _native.check(self.L.hg_forward_ragged(self.plan, mel.data_ptr(), sB, sC, sT, B, T, fr, out.data_ptr(),
                                                        out_dtype, float(out_scale), prec, ws, ws_bytes, st))
 
+    def forward_window(self, mel: torch.Tensor, out: torch.Tensor, skip: int, keep: int, out_dtype: int, out_scale: float,
+                       prec: int):
+        """hg_forward_window: samples [skip, skip+keep) of every item -> out[b, 0, :keep]; `out` may live on a
+        peer GPU (its stores then go over NVLink)."""
+        B, _, T = mel.shape
+        if out.device != mel.device:
+            _native.check(self.L.hg_enable_peer_access(mel.device.index, out.device.index))
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream().cuda_stream
+            ws, ws_bytes = self.workspace(B, T, prec, st)
+            sB, sC, sT = mel.stride()
+            _native.check(self.L.hg_forward_window(self.plan, mel.data_ptr(), sB, sC, sT, B, T, out.data_ptr(), out.stride(0),
+                                                   skip, keep, out_dtype, float(out_scale), prec, ws, ws_bytes, st))
+
     def halo_frames(self) -> int:
         n = ctypes.c_int()
         _native.check(self.L.hg_halo_frames(self.plan, ctypes.byref(n)))
@@ -286,6 +300,38 @@ class Generator(nn.Module):
         ``[i, 0, :frames[i]*hop]`` and zero beyond (from the next multiple of 256 samples on, when hop is
         not a multiple of the last kernel's 256-sample tile)."""
         return self._run(x, _native.OUT_F32, 1.0, frames)
+
+    @torch.no_grad()
+    def forward_into(self, x, out, skip_frames: int = 0, keep_frames: Optional[int] = None, max_wav_value: float = 32768.0):
+        """Run ``forward(x)`` and store only the samples of mel frames ``[skip_frames, skip_frames +
+        keep_frames)`` into ``out`` [B,1,keep_frames*hop] (float32, or int16 for the fused
+        ``* max_wav_value`` + cast) — the epilogue of the last kernel writes them in place, nothing else
+        is materialised.  This is how a time chunk computed with halo frames delivers its owned samples
+        straight into the final waveform (``parallel.chunked_forward_into``).  ``out`` may be a view into a
+        larger buffer (unit stride along time) and may live on ANOTHER GPU of the node, peer-mapped into
+        this process (``parallel.share_output_buffer``): the stores then travel over NVLink and no gather
+        collective is needed."""
+        if not isinstance(x, torch.Tensor) or x.dim() != 3 or x.shape[1] != NUM_MELS:
+            raise RuntimeError(f"expected input[B, {NUM_MELS}, T], got {list(getattr(x, 'shape', []))}")
+        eng = self._get_engine()
+        if x.device != eng.device:
+            raise RuntimeError(f"input is on {x.device} but the generator's weights are on {eng.device}")
+        B, _, T = x.shape
+        keep = T - skip_frames if keep_frames is None else int(keep_frames)
+        hop = self.hop_length
+        if skip_frames < 0 or keep < 1 or skip_frames + keep > T:
+            raise ValueError(f"frames [{skip_frames}, {skip_frames + keep}) outside the {T} frames of the input")
+        if out.dtype not in (torch.float32, torch.int16) or out.device.type != "cuda":
+            raise ValueError("out must be a CUDA float32 or int16 tensor")
+        if tuple(out.shape) != (B, 1, keep * hop) or out.stride(2) != 1:
+            raise ValueError(f"out must be [B={B}, 1, {keep * hop}] with unit stride along time, got {list(out.shape)} / {out.stride()}")
+        x = x.detach()
+        if x.dtype != torch.float32:
+            x = x.float()
+        i16 = out.dtype == torch.int16
+        eng.forward_window(x, out, skip_frames * hop, keep * hop, _native.OUT_I16 if i16 else _native.OUT_F32,
+                           float(max_wav_value) if i16 else 1.0, _native.PRECISIONS[self.precision])
+        return out
 
     @torch.no_grad()
     def make_graphed(self, B: int, T: int, out_int16: bool = False, max_wav_value: float = 32768.0):

@@ -115,6 +115,21 @@ def chunked_forward(forward_fn: Callable[[torch.Tensor], torch.Tensor], mel: tor
     return torch.cat(outs, dim=-1)
 
 
+def chunked_forward_into(generator, mel: torch.Tensor, chunk_frames: int, halo: int, out: torch.Tensor,
+                         max_wav_value: float = 32768.0) -> torch.Tensor:
+    """``chunked_forward`` without the concatenation: every chunk's last kernel stores its owned samples
+    directly at their place in ``out`` [B,1,T*hop] (``Generator.forward_into``), the halo samples are
+    never written.  ``out`` may be a window of a buffer on another GPU (see ``share_output_buffer``)."""
+    T = mel.shape[-1]
+    hop = generator.hop_length
+    parts = max(1, -(-T // max(1, chunk_frames)))
+    for c in plan_time_chunks(T, parts, halo):
+        if c.frames > 0:
+            generator.forward_into(mel[:, :, c.lo:c.hi], out[:, :, c.start * hop:c.stop * hop], c.start - c.lo, c.frames,
+                                   max_wav_value)
+    return out
+
+
 # ----------------------------------------------------------------------------- distributed pieces
 def exchange_halo(local_mel: torch.Tensor, halo: int, group=None) -> tuple:
     """Neighbour exchange for a mel that is already time-sharded across ranks.
@@ -161,6 +176,91 @@ def sharded_long_form(forward_fn: Callable[[torch.Tensor], torch.Tensor], local_
     y = forward_fn(padded)
     n = y.shape[-1]
     return y[..., left * hop:n - right * hop]
+
+
+class _PeerMapping:
+    """A buffer of another process's GPU mapped for this rank's GPU (hg_ipc_import); exposes
+    __cuda_array_interface__ so torch can alias it, closes the mapping when collected."""
+
+    def __init__(self, device_index: int, handle: bytes, offset: int, shape, typestr: str):
+        import ctypes
+
+        from . import _native
+
+        self._L = _native.lib()
+        self._device = device_index
+        base, ptr = ctypes.c_void_p(), ctypes.c_void_p()
+        _native.check(self._L.hg_ipc_import(device_index, handle, offset, ctypes.byref(base), ctypes.byref(ptr)))
+        self._base = base
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr.value, False), "version": 2}
+
+    def __del__(self):
+        try:
+            if self._base:
+                self._L.hg_ipc_close(self._device, self._base)
+                self._base = None
+        except Exception:
+            pass
+
+
+_TYPESTR = {torch.float32: "<f4", torch.int16: "<i2"}
+
+
+def share_output_buffer(shape, dtype=torch.float32, owner: int = 0, group=None) -> torch.Tensor:
+    """One waveform buffer on rank ``owner``'s GPU, writable by the kernels of every rank of the node:
+    the owner allocates it and exports it through CUDA IPC (``hg_ipc_export``), the handle travels over
+    the process group, and every other rank maps it for ITS OWN GPU (``hg_ipc_import``) and gets a
+    tensor that aliases the owner's memory (labelled with the local device; loads and stores go over
+    NVLink).  ``Generator.forward_into`` can then store waveform samples straight into it, which
+    replaces the gather collective of ``gather_wav``.  Single node only.  Keep the returned tensor
+    alive on every rank, and ``dist.barrier()`` after the last writer has synchronised, before the
+    owner reads."""
+    import ctypes
+
+    import torch.distributed as dist
+
+    from . import _native
+
+    rank = dist.get_rank(group)
+    local = torch.cuda.current_device()
+    box = [None]
+    buf = None
+    if rank == owner:
+        buf = torch.empty(*shape, dtype=dtype, device=torch.device("cuda", local))
+        handle = ctypes.create_string_buffer(64)
+        off = ctypes.c_int64()
+        _native.check(_native.lib().hg_ipc_export(buf.data_ptr(), handle, ctypes.byref(off)))
+        box[0] = (handle.raw, off.value)
+    dist.broadcast_object_list(box, src=_global_rank(owner, group), group=group)
+    if rank != owner:
+        handle, off = box[0]
+        mapping = _PeerMapping(local, handle, off, shape, _TYPESTR[dtype])
+        buf = torch.as_tensor(mapping, device=torch.device("cuda", local))
+        buf._hg_peer_mapping = mapping  # the mapping lives as long as the tensor that aliases it
+    return buf
+
+
+def sharded_long_form_into(generator, local_mel: torch.Tensor, halo: int, out_full: torch.Tensor, first_frame: int,
+                           chunk_frames: int = 16384, group=None, max_wav_value: float = 32768.0) -> None:
+    """Time-sharded long-form synthesis with the gather fused into the last kernel: halo exchange with the
+    neighbours, then this rank's frames ``[first_frame, first_frame + T_r)`` are vocoded chunk by chunk and
+    every chunk's samples are stored directly into ``out_full`` [B,1,T_total*hop] (``share_output_buffer``),
+    wherever that buffer lives."""
+    padded, left, right = exchange_halo(local_mel, halo, group)
+    hop = generator.hop_length
+    T_r = local_mel.shape[-1]
+    own = out_full[:, :, first_frame * hop:(first_frame + T_r) * hop]
+    Tp = padded.shape[-1]
+    parts = max(1, -(-T_r // max(1, chunk_frames)))
+    for c in plan_time_chunks(T_r, parts, halo):
+        if c.frames == 0:
+            continue
+        # chunk c owns local frames [c.start, c.stop); in `padded` they sit `left` frames further right, and the
+        # neighbours' halo frames stand in for the chunk halos at this rank's two ends
+        lo = max(0, c.start + left - halo)
+        hi = min(Tp, c.stop + left + halo)
+        generator.forward_into(padded[:, :, lo:hi], own[:, :, c.start * hop:c.stop * hop], c.start + left - lo, c.frames,
+                               max_wav_value)
 
 
 def gather_wav(local_wav: torch.Tensor, dst: int = 0, group=None) -> Optional[torch.Tensor]:
