@@ -193,6 +193,24 @@ def test_ragged_batch_is_bit_identical_inside_valid_ranges(prec):
         m.forward_ragged(mel, [0] + frames[1:])  # frames must be in [1, T]
 
 
+def test_ragged_batches_larger_than_the_kernel_limit_are_split():
+    """hg_forward_ragged takes at most 64 utterances (the tile table travels in the kernel parameters);
+    ragged_generate splits larger batches into groups of similar length."""
+    from tts_king_b200 import ragged
+
+    m = make_generator(fx.V1, precision="bf16").cuda()
+    B, T = 70, 24
+    mel = fx.synthetic_mel(B, T, seed=77).cuda()
+    keep = [((7 * i) % T + 1) * 256 - (i % 3) for i in range(B)]
+    with torch.no_grad():
+        full = m(mel)
+        parts = ragged.ragged_generate(m, mel, keep, out_int16=False)
+        with pytest.raises(ValueError):
+            m.forward_ragged(mel, [T] * B)
+    for i, n in enumerate(keep):
+        assert torch.equal(parts[i], full[i, 0, :n]), i
+
+
 @pytest.mark.parametrize("name,cfg", [("v2_narrow", fx.V2_NARROW), ("v3_rb2", fx.V3_RB2)])
 @pytest.mark.parametrize("prec", ["fp32", "bf16", "fp32_ffma"])
 def test_ragged_other_configs_and_paths(name, cfg, prec):
