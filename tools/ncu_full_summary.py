@@ -6,6 +6,8 @@
 Per captured launch: duration, DRAM traffic and throughput, tensor-pipe activity, and the occupancy of
 the L1 / shared-memory data pipe split by client — tensor-core operand reads (tc), LSU (shared +
 global) and TMA fills — which is the resource the 64/32-channel layers run out of.
+The TMA share is an estimate (fill bytes / 128 B per wavefront / elapsed cycles), so the three can
+add up to slightly more than 100 % on a saturated pipe.
 """
 import csv
 import sys
@@ -21,7 +23,6 @@ COLS = [
     ("tma fill GB", "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum"),
     ("smem bank conflicts M", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
     ("regs", "launch__registers_per_thread"),
-    ("smem KB", "launch__shared_mem_per_block_dynamic"),
     ("grid", "launch__grid_size"),
 ]
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
