@@ -614,8 +614,13 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
     }
     // CTA-pair kernel (conv_tc2.cu) for the wide same-length convs in bf16 mode
     // — whenever the single-CTA kernel could not keep the layer's weights resident in shared memory
-    if (plan->use_tc2 && tma_epi && !split && l.n_blocks == 1 && l.kc == 64 && (l.n_tile == 128 || l.n_tile == 256) &&
-        !choose_tiling(plan, l, split, slot).resident) {
+    // (its TMA epilogue also takes the MRF running sum as a second input tile, so the last conv of a
+    // ResBlock — xs += x, / num_kernels — stays on this path)
+    const bool tma_epi2 = plan->epi_tma && l.kind == L_CONV && l.cout % 16 == 0;
+    const int slot2 = std::max(1024, (epi.res ? 2048 : 0) + (epi.acc_in ? 2048 : 0) + (epi.out_x ? 2048 : 0) + (epi.out_a0 ? 1024 : 0));
+    if (plan->use_tc2 && tma_epi2 && !split && l.n_blocks == 1 && l.kc == 64 && (l.n_tile == 128 || l.n_tile == 256) &&
+        !choose_tiling(plan, l, split, tma_epi ? slot : 2048).resident) {
+      const int slot = slot2;  // shadows the single-CTA kernel's slot size inside this branch
       int min_off = l.tap_off[0], max_off = l.tap_off[0];
       for (int j = 1; j < l.ntaps; ++j) { min_off = std::min(min_off, l.tap_off[j]); max_off = std::max(max_off, l.tap_off[j]); }
       const int ms = l.n_tile == 256 ? 1 : 2;
@@ -638,11 +643,12 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
         p.nbuf = nbuf; p.stages = stages; p.n_blocks = 1;
         p.total_work = ragged_fill(&p.rag, rag, B, rows, 2 * ms * 128);
         p.epi = epi; p.epi_tma = 1; p.epi_slot_bytes = slot;
-        CUtensorMap maps[5];
+        CUtensorMap maps[6];
         int rc = make_operand_map(plan, in.a0, L_in, B, l.cin_pad, 64, box_rows, &maps[0]);
         if (rc) return rc;
         if ((rc = make_weight_map(plan, l.w_hi, static_cast<long long>(l.nc) * l.ntaps * l.n_tile, l.n_tile / 2, &maps[1]))) return rc;
-        maps[2] = maps[3] = maps[4] = maps[0];
+        maps[2] = maps[3] = maps[4] = maps[5] = maps[0];
+        if (epi.acc_in) { p.has_acc = 1; if ((rc = make_tile_map(plan, epi.acc_in, L_in, B, l.cout, 1, &maps[5]))) return rc; }
         if (epi.res) { p.has_res = 1; if ((rc = make_tile_map(plan, epi.res, L_in, B, l.cout, 1, &maps[2]))) return rc; }
         if (epi.out_x) { p.has_x = 1; if ((rc = make_tile_map(plan, epi.out_x, L_in, B, l.cout, 1, &maps[3]))) return rc; }
         if (epi.out_a0) { p.has_a = 1; if ((rc = make_tile_map(plan, epi.out_a0, L_in, B, l.cout, 2, &maps[4]))) return rc; }

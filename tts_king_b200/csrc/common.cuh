@@ -383,6 +383,7 @@ struct TcConvParams {
   int total_work;  // B * tiles_per_item * n_blocks
   int epi_tma;     // 1: TMA epilogue (residual tiles loaded, x / operand tiles stored by TMA); 0: generic
   int has_res, has_x, has_a;  // what the TMA epilogue reads / writes (maps are kernel arguments)
+  int has_acc;                // conv_tc2 only: the MRF running sum is a second TMA-loaded input tile
   int epi_slot_bytes;         // shared memory per epilogue warp (TMA: res | x | a_hi | a_lo tiles; generic: 2 KB)
   int desc_mode;  // how a tap's row shift enters the UMMA descriptor (see conv_tc.cu)
   long long* dbg;       // optional [grid][8] cycle counters (HG_TC_DEBUG_TIMING): MMA-warp wait breakdown

@@ -101,7 +101,8 @@ template <int N_T, int MS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc2Threads, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_x,
-                const __grid_constant__ CUtensorMap map_ahi, const TcConvParams p) {
+                const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_acc,
+                const TcConvParams p) {
   constexpr int KC = 64, ROWB = 128;
   constexpr int HALF_N = N_T / 2;
   constexpr int STAGE_BYTES = HALF_N * ROWB;     // this CTA's half of a weight tile
@@ -138,6 +139,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     prefetch_tensormap(&map_a);
     prefetch_tensormap(&map_w);
     if (p.has_res) prefetch_tensormap(&map_res);
+    if (p.has_acc) prefetch_tensormap(&map_acc);
     if (p.has_x) prefetch_tensormap(&map_x);
     if (p.has_a) prefetch_tensormap(&map_ahi);
   }
@@ -257,8 +259,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int quarter = warp & 3;
     const int sub = e >> 2;
     uint8_t* slot = epi_smem + e * p.epi_slot_bytes;
+    // slot: [residual in 2 KB] [MRF running sum in 2 KB] [x out 2 KB] [operand out 1 KB], each only if used
     const float* rb = reinterpret_cast<const float*>(slot);
-    float* xb = reinterpret_cast<float*>(slot + (p.has_res ? 2048 : 0));
+    const float* accb = reinterpret_cast<const float*>(slot + (p.has_res ? 2048 : 0));
+    float* xb = reinterpret_cast<float*>(slot + (p.has_res ? 2048 : 0) + (p.has_acc ? 2048 : 0));
+    const bool has_in = p.has_res || p.has_acc;
     uint8_t* ab_hi = reinterpret_cast<uint8_t*>(xb) + (p.has_x ? 2048 : 0);
     constexpr int ITEMS = MS * CHUNKS;
     const uint32_t acc_empty_leader0 = map_to_cta(&acc_empty[0], 0);
@@ -267,11 +272,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       int b, m0;
       tile_coords(work, b, m0);
       const int ms = j / CHUNKS, c0 = (j - ms * CHUNKS) * 16;
-      mbar_arrive_expect_tx(&res_bar[e], 2048);
-      tma_load_3d(slot, &map_res, &res_bar[e], c0, m0 + ms * 128 + quarter * 32, b);
+      mbar_arrive_expect_tx(&res_bar[e], (p.has_res ? 2048 : 0) + (p.has_acc ? 2048 : 0));
+      if (p.has_res) tma_load_3d(slot, &map_res, &res_bar[e], c0, m0 + ms * 128 + quarter * 32, b);
+      if (p.has_acc)
+        tma_load_3d(slot + (p.has_res ? 2048 : 0), &map_acc, &res_bar[e], c0, m0 + ms * 128 + quarter * 32, b);
     };
     uint32_t res_uses = 0;
-    if (p.has_res && lane == 0 && sub < ITEMS && pair < p.total_work) prefetch_res(pair, sub);
+    if (has_in && lane == 0 && sub < ITEMS && pair < p.total_work) prefetch_res(pair, sub);
     const uint32_t swz64 = (lane >> 1) & 3, swz32 = (lane >> 2) & 1;
     int it = 0;
     for (int work = pair; work < p.total_work; work += npairs, ++it) {
@@ -304,13 +311,23 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           const float4 bb = *reinterpret_cast<const float4*>(p.epi.bias + c0 + 4 * q);
           v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
         }
-        if (p.has_res) {
+        if (has_in) {
           mbar_wait(&res_bar[e], res_uses & 1);
           ++res_uses;
+          if (p.has_res) {  // x = xt + x   (hifi/models.py:94)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 t = *reinterpret_cast<const float4*>(rb + lane * 16 + ((q ^ swz64) << 2));
-            v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+            for (int q = 0; q < 4; ++q) {
+              const float4 t = *reinterpret_cast<const float4*>(rb + lane * 16 + ((q ^ swz64) << 2));
+              v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+            }
+          }
+          if (p.has_acc) {  // xs += resblock(x)   (:193-195), same operand order as epilogue_rows
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 t = *reinterpret_cast<const float4*>(accb + lane * 16 + ((q ^ swz64) << 2));
+              v[4 * q] = t.x + v[4 * q]; v[4 * q + 1] = t.y + v[4 * q + 1];
+              v[4 * q + 2] = t.z + v[4 * q + 2]; v[4 * q + 3] = t.w + v[4 * q + 3];
+            }
           }
           fence_proxy_async();
           __syncwarp();
@@ -318,6 +335,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             if (j + 4 < ITEMS) prefetch_res(work, j + 4);
             else if (work + npairs < p.total_work) prefetch_res(work + npairs, sub);
           }
+        }
+        if (p.epi.post_div > 0.f) {  // x = xs / num_kernels   (:196)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __fdiv_rn(v[i], p.epi.post_div);
         }
         if (lane == 0) tma_store_wait_read();
         __syncwarp();
@@ -384,7 +405,7 @@ static cudaError_t launch_tc2(const CUtensorMap* maps, const TcConvParams& p, si
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  return cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
 }
 
 // maps: [0] operand (bf16), [1] packed weights (2-D), [2] residual, [3] x out, [4] a out.  grid must be even.
