@@ -21,40 +21,39 @@ from .hifi.models import Generator
 
 
 class AttrDict(dict):
-    def __init__(self, *args, **kwargs):
-        super(AttrDict, self).__init__(*args, **kwargs)
-        self.__dict__ = self
+    """dict whose keys are also attributes (the helper the reference keeps next to its wrapper,
+    hifiapi.py:5-8) — configs built by hand use it in place of OmegaConf."""
+
+    def __init__(self, *a, **kw):
+        dict.__init__(self, *a, **kw)
+        object.__setattr__(self, "__dict__", self)
 
 
 class HIFIapi:
     def __init__(self, config, device="gpu", compute_device=None, precision="fp32"):
-        if config.model_config["vocoder"]["use_cpu"]:
-            device = "cpu"
-        if device == "gpu":  # the reference's default is not a torch device name
-            device = "cuda"
-        if compute_device is None:
-            compute_device = device if str(device).startswith("cuda") else "cuda"
+        caller_side = "cpu" if config.model_config["vocoder"]["use_cpu"] else device
+        if caller_side == "gpu":  # the reference's default argument is not a torch device name
+            caller_side = "cuda"
         if not torch.cuda.is_available():
             raise RuntimeError("tts_king_b200.HIFIapi needs a CUDA (sm_100a) device; there is no CPU fallback")
+        if compute_device is None:
+            compute_device = caller_side if str(caller_side).startswith("cuda") else "cuda"
         compute_device = torch.device(compute_device)
         if compute_device.index is None:
             compute_device = torch.device("cuda", torch.cuda.current_device())
 
-        # Load checkpoint if exists
-        weights_path = config.hifi.weights_path
+        generator = Generator(config.hifi, precision=precision)
+        ckpt_path = config.hifi.weights_path  # optional {"generator": state_dict} file (hifiapi.py:17-22)
+        if ckpt_path is not None:
+            state = torch.load(ckpt_path, map_location="cpu")["generator"]
+            generator.load_state_dict(state)
+        generator.to(compute_device)
+        generator.remove_weight_norm()
 
-        self.model = Generator(config.hifi, precision=precision)
-        if weights_path is not None:
-            checkpoint = torch.load(weights_path, map_location="cpu")
-            self.model.load_state_dict(checkpoint["generator"])
-
+        self.model = generator.eval()
         self.cfg = config
-        self.device = device
+        self.device = caller_side
         self.compute_device = compute_device
-
-        self.model.to(compute_device)
-        self.model.remove_weight_norm()
-        self.model.eval()
 
     def train(self):
         raise NotImplementedError(" Train for HiFi was not implemented yet")
@@ -70,10 +69,10 @@ class HIFIapi:
         (numpy), like the reference: wav * MAX_WAV_VALUE, truncating cast.  The scale and cast are
         fused into the last kernel, so only 2 bytes per sample cross PCIe.
         """
-        self.model.eval()
+        scale = float(self.cfg.hifi.MAX_WAV_VALUE)
         with torch.no_grad():
             mel_dev = mel_specs.to(self.compute_device, non_blocking=True)
-            audio = self.model.generate_int16(mel_dev, float(self.cfg.hifi.MAX_WAV_VALUE))
+            audio = self.model.eval().generate_int16(mel_dev, scale)
             # device -> pinned host at full PCIe rate (a pageable .cpu() is staged and ~3x slower); the
             # pinned block comes from torch's caching host allocator and is owned by the returned array
             host = torch.empty(audio.shape, dtype=audio.dtype, pin_memory=True)
