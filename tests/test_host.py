@@ -52,6 +52,22 @@ def test_load_state_dict_both_layouts_and_strictness():
         m.load_state_dict(bad)
 
 
+def test_module_survives_deepcopy_and_pickle():
+    """The reference's AttrDict (`self.__dict__ = self`) loses its attributes when copied; the module keeps
+    the hyper-parameters it needs as plain values, so a copied / pickled generator still builds its plan."""
+    import copy
+    import pickle
+
+    m = make_generator(fx.TINY_RB1)
+    for clone in (copy.deepcopy(m), pickle.loads(pickle.dumps(m))):
+        assert clone.hop_length == 256 and clone.halo_frames == 13
+        c = clone._native_config()
+        assert c.upsample_initial_channel == 32 and c.num_upsamples == 4 and c.resblock_type == 1
+        assert list(c.upsample_rates)[:4] == [8, 8, 2, 2] and list(c.resblock_kernel_sizes)[:3] == [3, 7, 11]
+        for (k1, v1), (k2, v2) in zip(m.state_dict().items(), clone.state_dict().items()):
+            assert k1 == k2 and torch.equal(v1, v2)
+
+
 def test_get_padding():
     assert [get_padding(k, d) for k in (3, 7, 11) for d in (1, 3, 5)] == [1, 3, 5, 3, 9, 15, 5, 15, 25]
 

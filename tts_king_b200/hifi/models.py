@@ -14,6 +14,7 @@ Inference only: the output never requires grad.  CUDA only: a CPU tensor raises.
 from __future__ import annotations
 
 import ctypes
+import types
 from typing import Sequence, Dict, List, Optional, Tuple
 
 import torch
@@ -242,6 +243,14 @@ class Generator(nn.Module):
     def __init__(self, h, precision: str = "fp32"):
         super().__init__()
         self.h = h
+        # the hyper-parameters this module reads, as plain values: `h` is whatever object the caller has
+        # (OmegaConf node, AttrDict, namespace) and may not survive a deepcopy / pickle of the module
+        self._hp = types.SimpleNamespace(
+            resblock=str(h.resblock), upsample_initial_channel=int(h.upsample_initial_channel),
+            upsample_rates=tuple(int(u) for u in h.upsample_rates),
+            upsample_kernel_sizes=tuple(int(k) for k in h.upsample_kernel_sizes),
+            resblock_kernel_sizes=tuple(int(k) for k in h.resblock_kernel_sizes),
+            resblock_dilation_sizes=tuple(tuple(int(d) for d in ds) for ds in h.resblock_dilation_sizes))
         self.num_kernels = len(h.resblock_kernel_sizes)
         self.num_upsamples = len(h.upsample_rates)
         uic = h.upsample_initial_channel
@@ -368,9 +377,17 @@ class Generator(nn.Module):
     @property
     def hop_length(self) -> int:
         n = 1
-        for u in self.h.upsample_rates:
-            n *= int(u)
+        for u in self._hp.upsample_rates:
+            n *= u
         return n
+
+    @property
+    def halo_frames(self) -> int:
+        """Mel frames of context a sample needs on each side (13 for V1): the receptive reach of the
+        stack in frames — what time chunks and ragged batches add to the frames they own."""
+        from .. import parallel
+
+        return parallel.halo_frames(self._hp)
 
     def kernel_launches(self, B: int, T: int) -> int:
         """Kernels one forward enqueues (bench.py reports it as gpu_launches)."""
@@ -419,7 +436,7 @@ class Generator(nn.Module):
         return out
 
     def _native_config(self) -> _native.HgConfig:
-        h = self.h
+        h = self._hp
         c = _native.HgConfig()
         c.num_mels = NUM_MELS
         c.upsample_initial_channel = int(h.upsample_initial_channel)

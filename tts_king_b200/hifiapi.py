@@ -22,11 +22,23 @@ from .hifi.models import Generator
 
 class AttrDict(dict):
     """dict whose keys are also attributes (the helper the reference keeps next to its wrapper,
-    hifiapi.py:5-8) — configs built by hand use it in place of OmegaConf."""
+    hifiapi.py:5-8) — configs built by hand use it in place of OmegaConf.  Attribute access is routed
+    to the items, so copies and pickles of a config (and of a module holding one) keep working."""
 
-    def __init__(self, *a, **kw):
-        dict.__init__(self, *a, **kw)
-        object.__setattr__(self, "__dict__", self)
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError:
+            raise AttributeError(name) from None
+
+    def __setattr__(self, name, value):
+        self[name] = value
+
+    def __delattr__(self, name):
+        try:
+            del self[name]
+        except KeyError:
+            raise AttributeError(name) from None
 
 
 class HIFIapi:

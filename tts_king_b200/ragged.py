@@ -67,6 +67,11 @@ def bucket_extent(frames: Sequence[int], bucket: Sequence[int], halo: int, t_max
     return min(int(t_max), max(int(frames[i]) for i in bucket) + halo)
 
 
+def _halo_of(generator) -> int:
+    h = getattr(generator, "halo_frames", None)
+    return int(h) if h is not None else parallel.halo_frames(generator.h)
+
+
 @torch.no_grad()
 def ragged_generate(generator, mels: torch.Tensor, sample_lengths: Sequence[int], out_int16: bool = True,
                     max_wav_value: float = 32768.0, launch_cost: int = 400, mode: str = "auto") -> List[torch.Tensor]:
@@ -96,14 +101,14 @@ def ragged_generate(generator, mels: torch.Tensor, sample_lengths: Sequence[int]
             whole = len(group) == B
             x = mels if whole else mels.index_select(0, torch.as_tensor(group, device=mels.device))
             tg = max(frames[i] for i in group)
-            tg = min(T, tg + parallel.halo_frames(generator.h))
+            tg = min(T, tg + _halo_of(generator))
             fr = [frames[i] for i in group]
             y = (generator.generate_int16(x[:, :, :tg], max_wav_value, frames=fr) if out_int16
                  else generator.forward_ragged(x[:, :, :tg], fr))
             for row, i in enumerate(group):
                 out[i] = y[row, 0, :keep[i]]
         return out  # type: ignore[return-value]
-    halo = parallel.halo_frames(generator.h)
+    halo = _halo_of(generator)
     run = (lambda x: generator.generate_int16(x, max_wav_value)) if out_int16 else generator
     for bucket in plan_length_buckets(frames, halo, T, launch_cost):
         tb = bucket_extent(frames, bucket, halo, T)
