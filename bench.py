@@ -162,6 +162,38 @@ def conv_flops(row, B, frames_in):
     return 2.0 * B * frames_in * row["c_in"] * row["c_out"] * row["k"]
 
 
+def layer_bytes(row, names, B, T, rates, e_a=2):
+    """Algorithmic HBM bytes of one launch under this implementation's dataflow: operand
+    copies `a` are e_a bytes per element (2 = one bf16 plane, 4 = hi + lo planes), the residual stream is
+    fp32; unique elements read + written, halo re-reads and weights excluded."""
+    import math
+
+    n = row["name"]
+    if row["kind"] < 0:
+        return B * T * (80 * 4 + 128 * e_a)
+    cin, cout = row["c_in"], row["c_out"]
+    if n == "conv_pre":
+        return B * T * (128 * e_a + cout * e_a)
+    if n.startswith("ups."):
+        i = int(n.split(".")[1])
+        lin = T * math.prod(rates[:i])
+        return B * (lin * cin * e_a + lin * row["stride"] * cout * (4 + e_a))
+    if n == "conv_post":
+        return B * T * math.prod(rates) * (cin * 4 + 4)
+    blk = int(n.split(".")[1])
+    nk = 3  # ResBlocks per stage (num_kernels of V1 / V2-style configs)
+    i, j = blk // nk, blk % nk
+    e = B * T * math.prod(rates[:i + 1]) * cout
+    if ".convs1." in n:
+        return e * (e_a + e_a)                       # a in, t out
+    by = e * (e_a + 4)                               # operand in + residual in
+    if not n.endswith(".2"):
+        return by + e * (4 + e_a)                    # x out + a out
+    by += e * (4 if j > 0 else 0)                    # last pair of the block: MRF running sum in
+    by += e * (4 if (j < nk - 1 or i == len(rates) - 1) else e_a)  # sum / x out, or the next stage's operand
+    return by
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -278,6 +310,15 @@ def main():
             r["tflops"] = r["flops"] / (r["ms"] * 1e-3) / 1e12 if r["ms"] > 0 else None
             if r.get("tensor_core"):
                 tc_flops += r["flops"]; tc_ms += r["ms"]
+        # every launch against its own roofline: max(FLOPs / tensor peak, algorithmic bytes / HBM peak)
+        e_a = 4 if args.precision == "fp32" else 2
+        tf_peak = float(peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"])) * 1e12
+        bw_peak = float(peaks.get("hbm_gbs", 6555.8)) * 1e9
+        roof_ms = 0.0
+        for r in rows:
+            r["bytes"] = layer_bytes(r, names, B_PER_GPU, T_FRAMES, rates, e_a)
+            r["roofline_ms"] = max(r.get("flops", 0.0) / tf_peak, r["bytes"] / bw_peak) * 1e3
+            roof_ms += r["roofline_ms"]
         mult = 3.0 if args.precision == "fp32" else 1.0  # bf16x3: compensation passes are overhead, not credited
         peak = float(peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"]))
         ach = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
@@ -292,7 +333,10 @@ def main():
                     "hbm_floor_ms": (traffic / (float(peaks.get("hbm_gbs", 6555.8)) * 1e9) * 1e3) if traffic else None,
                     "tensor_floor_ms": tc_flops / (peak * 1e12) * 1e3, "measured_ms": tc_ms, "kernel": "conv_tc2_kernel + conv_pair_tc_kernel + conv_tc_kernel (tcgen05 implicit-GEMM convs, all 59 launches of a step)",
                     "share_of_step": tc_ms / all_ms if all_ms else None, "peak_source": peaks["_source"] + " sustained bf16",
-                    "mma_passes_per_product": mult}
+                    "mma_passes_per_product": mult,
+                    "per_layer": {"sum_of_launch_rooflines_ms": roof_ms, "sum_of_launch_times_ms": all_ms,
+                                  "frac": roof_ms / all_ms if all_ms else None,
+                                  "note": "each launch's roofline = max(algorithmic FLOPs / tensor peak, algorithmic bytes / HBM peak)"}}
         layers_out = rows
         try:
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

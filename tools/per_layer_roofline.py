@@ -14,6 +14,8 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bench import layer_bytes  # noqa: E402  (one model of the dataflow for the bench line and this table)
 rows = json.load(open(sys.argv[1]))
 B, T = 16, 800
 rates = [8, 8, 2, 2]
@@ -26,34 +28,22 @@ print("|---|---|---|---|---|---|---|---|---|---|---|")
 tot_ms = tot_roof = 0.0
 for r in rows:
     n = r["name"]
+    by = layer_bytes(r, names, B, T, rates, 2)
     if r["kind"] < 0:
-        by = B * T * (80 * 4 + 128 * 2); fl = 0; shape = "mel [16,80,800]"; path = "mel_to_operand"
+        fl = 0; shape = "mel [16,80,800]"; path = "mel_to_operand"
     else:
         cin, cout, k = r["c_in"], r["c_out"], r["k"]
         if n == "conv_pre":
-            L = T; fl = 2 * B * L * cin * cout * k; by = B * L * (128 * 2 + cout * 2)
+            fl = 2 * B * T * cin * cout * k
         elif n.startswith("ups."):
-            i = int(n.split(".")[1]); Lin = T * math.prod(rates[:i]); Lout = Lin * r["stride"]
-            fl = 2 * B * Lin * cin * cout * k; by = B * (Lin * cin * 2 + Lout * cout * 6)
+            i = int(n.split(".")[1]); fl = 2 * B * T * math.prod(rates[:i]) * cin * cout * k
         elif n == "conv_post":
-            L = T * 256; fl = 2 * B * L * cin * k; by = B * L * (cin * 4 + 4)
+            fl = 2 * B * T * 256 * cin * k
         else:
-            blk = int(n.split(".")[1]); i = blk // 3; L = T * math.prod(rates[:i + 1]); e = B * L * cout
-            fl = 2 * e * cin * k
-            pair = ".convs2." in n and n.replace(".convs2.", ".convs1.") not in names
-            last = n.endswith(".2")  # last pair of the block: MRF combine fused
-            if ".convs1." in n:
-                by = e * (2 + 2)
-            else:
-                by = e * (2 + 4)                      # operand in + residual in
-                if pair:
-                    fl *= 2
-                if not last:
-                    by += e * (4 + 2)                 # x out + a out
-                else:
-                    j = blk % 3
-                    by += e * (4 if j > 0 else 0)     # xs in
-                    by += e * (4 if (j < 2 or i == 3) else 2)  # xs / x out, or next-stage operand out
+            i = int(n.split(".")[1]) // 3
+            fl = 2 * B * T * math.prod(rates[:i + 1]) * cout * cin * k
+            if ".convs2." in n and n.replace(".convs2.", ".convs1.") not in names:
+                fl *= 2
         shape = f"{cin}->{cout} k{k}" + (f" d{r['dilation']}" if r["kind"] == 0 else f" s{r['stride']}")
         path = r.get("kernel") or ("conv_pair_tc (fused pair)" if (".convs2." in n and n.replace(".convs2.", ".convs1.") not in names) else (
             "tcgen05" if r.get("tensor_core") else "cuda-core"))
