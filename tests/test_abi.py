@@ -31,9 +31,32 @@ def test_library_exports_every_declared_symbol():
     assert _native.lib().hg_abi_version() == 1
 
 
-def test_struct_layout_matches_header():
+def test_struct_layout_matches_header(tmp_path):
     # 3 + 8 + 8 + 1 + 8 + 8*4 + 1 int32 fields
     assert ctypes.sizeof(_native.HgConfig) == 4 * (3 + 8 + 8 + 1 + 8 + 32 + 1)
+    # the header itself, through a C compiler: it must be plain C (no C++-isms) and the ctypes mirrors of
+    # its structs must have the same size and field offsets
+    import shutil
+    import subprocess
+
+    cc = shutil.which("gcc", path="/usr/bin:/bin") or shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "layout.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "hifigan_b200.h"\n'
+        "int main(void) {\n"
+        '  printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(HgConfig), sizeof(HgLayerInfo), sizeof(HgStackLayer),\n'
+        "         offsetof(HgConfig, resblock_dilation_sizes), offsetof(HgLayerInfo, kernel_path),\n"
+        "         offsetof(HgLayerInfo, n_tile), offsetof(HgStackLayer, slope));\n"
+        "  return (HG_PATH_REPACK == 6 && HG_ACT_TANH == 2 && HG_OUT_I16 != HG_OUT_F32) ? 0 : 1;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    want = [ctypes.sizeof(_native.HgConfig), ctypes.sizeof(_native.HgLayerInfo), ctypes.sizeof(_native.HgStackLayer),
+            _native.HgConfig.resblock_dilation_sizes.offset, _native.HgLayerInfo.kernel_path.offset,
+            _native.HgLayerInfo.n_tile.offset, _native.HgStackLayer.slope.offset]
+    assert [int(v) for v in out] == want
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
