@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """One warm-up forward + one profiled forward of the bench workload (HiFi-GAN V1, 16 x 800 frames),
-for ncu.  No torch kernels are launched: every launch ncu sees is one of ours (79 per forward:
-mel_to_operand, 77 x conv_tc_kernel, conv_post_kernel).
+for ncu.  No torch kernels are launched: every launch ncu sees is one of ours — 61 per forward in bf16
+mode (mel_to_operand, 30 x conv_tc2_kernel, 18 x conv_pair_tc_kernel, 11 x conv_tc_kernel,
+conv_post32_kernel), 79 in fp32 mode (no pair fusion, no CTA-pair kernel).
 
-    ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 79 --launch-count 79 \
+    ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 61 --launch-count 61 \
         --csv --log-file gpurun_out/launches.csv python tools/ncu_one_forward.py [bf16|fp32]
 """
 import os
