@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """One warm-up forward + one profiled forward of the bench workload (HiFi-GAN V1, 16 x 800 frames),
 for ncu.  No torch kernels are launched: every launch ncu sees is one of ours — 61 per forward in bf16
-mode (mel_to_operand, 30 x conv_tc2_kernel, 18 x conv_pair_tc_kernel, 11 x conv_tc_kernel,
+mode (mel_to_operand, the tcgen05 kernels conv_tc2_kernel / conv_pair_tc_kernel / conv_tc_kernel,
 conv_post32_kernel), 79 in fp32 mode (no pair fusion, no CTA-pair kernel).
 
     ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 61 --launch-count 61 \
