@@ -122,6 +122,7 @@ def cpu_reference_step(n_utt: int, frames: int, threads: int):
 
     def step():
         y = torch_oracle.forward(fx.V1, sd, mel)
+        step.last_float, step.mel = y, mel  # kept for the fp32-accuracy record (checker use, outside any timed GPU region)
         return (y * 32768).numpy().astype("int16")
 
     return step, n_utt * frames * HOP / SR
@@ -194,6 +195,162 @@ def layer_bytes(row, names, B, T, rates, e_a=2):
     return by
 
 
+def layer_bytes_8d(row, names, B, T, rates, e=2):
+    """Algorithmic HBM bytes of one launch by SURVEY.md §8(d)'s own rule: (unique input + unique output
+    elements) x the storage dtype (e = 2 for the bf16 path, 4 for fp32) + one more C*L*e for a fused residual
+    read and for a fused MRF accumulate read; a fused ResBlock-pair launch counts its own in / out / residual
+    only (the intermediate never leaves the SM).  Weights and halo re-reads excluded."""
+    import math
+
+    n = row["name"]
+    if row["kind"] < 0:
+        return B * T * 80 * (4 + e)
+    cin, cout = row["c_in"], row["c_out"]
+    if n == "conv_pre":
+        return B * T * (80 + cout) * e
+    if n.startswith("ups."):
+        i = int(n.split(".")[1])
+        lin = T * math.prod(rates[:i])
+        return B * lin * (cin + row["stride"] * cout) * e
+    if n == "conv_post":
+        return B * T * math.prod(rates) * (cin + 1) * e
+    blk = int(n.split(".")[1])
+    nk = 3
+    i, j = blk // nk, blk % nk
+    el = B * T * math.prod(rates[:i + 1]) * cout
+    if ".convs1." in n:
+        return 2 * el * e
+    by = 3 * el * e                                   # in + out + fused residual read
+    if n.endswith(".2") and j > 0:
+        by += el * e                                  # fused MRF accumulate read
+    return by
+
+
+def timed_max_over_ranks(fn, reps, world, dist, dev):
+    """Mean device time of `reps` calls of fn (CUDA events on the current stream, barrier + synchronize on
+    both sides), MAX over ranks; returns (ms per call, last result)."""
+    import torch
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = None
+    for _ in range(reps):
+        out = fn()
+    e1.record()
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), out
+
+
+def run_cfg3_strong(gen, dev, world, rank, dist, reps=3):
+    """BASELINE cfg-3: 64 utterances x 2000 frames in TOTAL, utterance-sharded over the ranks (greedy
+    longest-first, tts_king_b200.parallel.shard_utterances) — strong scaling, no data-path collective."""
+    import torch
+
+    from tts_king_b200 import parallel
+
+    lengths = [2000] * 64
+    mine = parallel.shard_utterances(lengths, world)[rank]
+    mel = torch.randn(len(mine), 80, 2000, generator=torch.Generator().manual_seed(300 + rank)).to(dev)
+    with torch.no_grad():
+        y = gen(mel)                                  # warm-up (workspace, descriptors)
+        ok = bool(torch.equal(y[:1], gen(mel[:1])))   # an item's samples do not depend on its batch
+        del y
+        sampler = ClockSampler(dev.index)
+        if rank == 0:
+            sampler.start()
+        ms, _ = timed_max_over_ranks(lambda: gen(mel), reps, world, dist, dev)
+        clocks = sampler.stop() if rank == 0 else None
+    flags = torch.tensor([1 if ok else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    audio_s = sum(lengths) * HOP / SR
+    del mel
+    torch.cuda.empty_cache()
+    return {"workload": "64 utterances x 2000 frames in total, utterance-sharded", "scaling": "strong", "n_gpus": world,
+            "utterances_per_rank": len(mine), "ms": ms, "reps": reps, "audio_sec_per_sec": audio_s / (ms * 1e-3),
+            "item_bitwise_equal_to_its_single_forward": bool(flags.item()), "clocks": clocks}
+
+
+def run_long_form(gen, dev, world, rank, dist, reps=2, T=310078, sub=16384):
+    """BASELINE cfg-5: ONE 60-minute mel (310 078 frames) time-sharded over the ranks.  Every step: 13-frame
+    mel halo exchange with the neighbours (NCCL isend/irecv), the rank's frames vocoded in 16 384-frame
+    chunks, and the waveform collected on rank 0 — (a) with an NCCL gather, (b) with the gather fused into
+    conv_post's stores (rank 0's buffer peer-mapped over NVLink, CUDA IPC).  Rank 0 then recomputes, on
+    its own GPU alone, the samples around every rank boundary and both ends and compares bit for bit."""
+    import torch
+
+    from tts_king_b200 import parallel
+
+    halo, hop = gen.halo_frames, gen.hop_length
+    mel_full = torch.randn(1, 80, T, generator=torch.Generator().manual_seed(5000))  # same on every rank
+    chunks = parallel.plan_time_chunks(T, world, 0)
+    c = chunks[rank]
+    local_mel = mel_full[:, :, c.start:c.stop].contiguous().to(dev)  # the mel arrives already time-sharded
+    audio_s = T * hop / SR
+    rec = {"workload": f"one mel of {T} frames (60 min at 22.05 kHz), time-sharded", "scaling": "strong", "n_gpus": world,
+           "frames_per_rank": c.frames, "chunk_frames": sub, "halo_frames": halo,
+           "halo_bytes": 0 if world == 1 else 2 * (world - 1) * halo * 80 * 4,
+           "gather_bytes": 0 if world == 1 else int(sum(ch.frames for ch in chunks[1:])) * hop * 4, "reps": reps}
+
+    def check(wav):
+        """rank 0: windows straddling every rank boundary and both ends, recomputed on one GPU."""
+        ok = True
+        with torch.no_grad():
+            for e in [0] + [ch.stop for ch in chunks[:-1]] + [T]:
+                a, b = max(0, e - 40), min(T, e + 40)
+                lo, hi = max(0, a - halo), min(T, b + halo)
+                w = gen(mel_full[:, :, lo:hi].to(dev))
+                ok = ok and bool(torch.equal(wav[:, :, a * hop:b * hop], w[:, :, (a - lo) * hop:(b - lo) * hop]))
+        return ok
+
+    with torch.no_grad():
+        if world == 1:
+            out = torch.empty((1, 1, T * hop), device=dev)
+            fn = lambda: parallel.chunked_forward_into(gen, local_mel, sub, halo, out)  # noqa: E731
+            fn()
+            ms, _ = timed_max_over_ranks(fn, reps, world, dist, dev)
+            rec.update(ms=ms, audio_sec_per_sec=audio_s / (ms * 1e-3), variant="single GPU, chunked, conv_post stores in place",
+                       bitwise_equal_to_single_gpu=check(out))
+            return rec
+
+        def run_nccl():
+            padded, left, right = parallel.exchange_halo(local_mel, halo)
+            y = parallel.chunked_forward(gen, padded, sub, halo, hop)
+            y = y[..., left * hop: y.shape[-1] - right * hop]
+            return parallel.gather_wav(y, dst=0)
+
+        run_nccl()
+        ms_nccl, wav = timed_max_over_ranks(run_nccl, reps, world, dist, dev)
+        ok_nccl = check(wav) if rank == 0 else True
+        del wav
+        full = parallel.share_output_buffer((1, 1, T * hop), torch.float32, owner=0)
+        run_direct = lambda: parallel.sharded_long_form_into(gen, local_mel, halo, full, c.start, chunk_frames=sub)  # noqa: E731
+        run_direct()
+        ms_direct, _ = timed_max_over_ranks(run_direct, reps, world, dist, dev)
+        ok_direct = check(full) if rank == 0 else True
+        dist.barrier()
+        del full
+    flags = torch.tensor([1 if (ok_nccl and ok_direct) else 0], device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    ms = min(ms_nccl, ms_direct)
+    rec.update(ms=ms, audio_sec_per_sec=audio_s / (ms * 1e-3), ms_nccl_halo_and_gather=ms_nccl,
+               ms_halo_and_direct_nvlink_store=ms_direct,
+               variant="nccl gather" if ms_nccl <= ms_direct else "direct NVLink store from conv_post",
+               bitwise_equal_to_single_gpu=bool(flags.item()))
+    torch.cuda.empty_cache()
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -202,6 +359,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the cfg-3 / cfg-5 / fp32 records")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -314,11 +472,14 @@ def main():
         e_a = 4 if args.precision == "fp32" else 2
         tf_peak = float(peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"])) * 1e12
         bw_peak = float(peaks.get("hbm_gbs", 6555.8)) * 1e9
-        roof_ms = 0.0
+        roof_ms = roof8d_ms = 0.0
         for r in rows:
             r["bytes"] = layer_bytes(r, names, B_PER_GPU, T_FRAMES, rates, e_a)
             r["roofline_ms"] = max(r.get("flops", 0.0) / tf_peak, r["bytes"] / bw_peak) * 1e3
             roof_ms += r["roofline_ms"]
+            r["bytes_8d"] = layer_bytes_8d(r, names, B_PER_GPU, T_FRAMES, rates, e_a)
+            r["roofline_8d_ms"] = max(r.get("flops", 0.0) / tf_peak, r["bytes_8d"] / bw_peak) * 1e3
+            roof8d_ms += r["roofline_8d_ms"]
         mult = 3.0 if args.precision == "fp32" else 1.0  # bf16x3: compensation passes are overhead, not credited
         peak = float(peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"]))
         ach = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
@@ -336,7 +497,10 @@ def main():
                     "mma_passes_per_product": mult,
                     "per_layer": {"sum_of_launch_rooflines_ms": roof_ms, "sum_of_launch_times_ms": all_ms,
                                   "frac": roof_ms / all_ms if all_ms else None,
-                                  "note": "each launch's roofline = max(algorithmic FLOPs / tensor peak, algorithmic bytes / HBM peak)"}}
+                                  "note": "each launch's roofline = max(algorithmic FLOPs / tensor peak, bytes / HBM peak); `frac` counts "
+                                          "the bytes of THIS implementation's dataflow (fp32 residual stream + a separate bf16 operand copy), "
+                                          "`frac_8d` counts SURVEY.md §8(d)'s algorithmic bytes (every tensor once, in the path's storage dtype)",
+                                  "sum_of_launch_rooflines_8d_ms": roof8d_ms, "frac_8d": roof8d_ms / all_ms if all_ms else None}}
         layers_out = rows
         try:
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
@@ -345,7 +509,7 @@ def main():
             pass
 
     # ---------------- CPU baseline on this box's host cores (rank 0, N = 1 only)
-    cpu_baseline = None
+    cpu_baseline = step = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         step, a_s = cpu_reference_step(1, T_FRAMES, threads)
@@ -358,6 +522,33 @@ def main():
         cpu_baseline = {"value": a_s / best, "unit": "audio-s/s", "cores": threads, "kind": "port",
                         "sample": f"1 utterance x {T_FRAMES} frames, best of {reps} (torch/oneDNN fp32, "
                                   "oracle.torch_oracle = the ATen calls hifi/models.py dispatches)"}
+
+    # ---------------- the other BASELINE configs, so that the driver's N = 1/2/4/8 runs carry them: the
+    # fp32-accurate arithmetic mode on the same workload, cfg-3 (strong scaling over utterances) and cfg-5
+    # (one long mel, halo exchange + gather) — every rank takes part
+    fp32_rec = cfg3 = long_form = None
+    if not args.no_extras:
+        if args.precision == "bf16":
+            gen.precision = "fp32"
+            with torch.no_grad():
+                for _ in range(3):
+                    gen(mel_dev)
+                ms32, _ = timed_max_over_ranks(lambda: gen(mel_dev), 10, world, dist if world > 1 else None, dev)
+                err = None
+                if cpu_baseline is not None:  # N = 1: the oracle's waveform of the timed CPU sample is at hand
+                    y = gen(step.mel.to(dev)).cpu()
+                    err = float((y - step.last_float).abs().max())
+            gen.precision = "bf16"
+            peaks = load_peaks()
+            tf = world * B_PER_GPU * T_FRAMES * FLOP_PER_FRAME_V1 / (ms32 * 1e-3) / 1e12
+            pk = float(peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"])) * world
+            fp32_rec = {"value": world * audio_s_step / (ms32 * 1e-3), "unit": "audio-s/s", "ms_per_step": ms32, "steps": 10,
+                        "dtype": "bf16x3 split products, fp32 accumulate (fp32-accurate mode, north_star <= 1e-4)",
+                        "max_abs_vs_oracle": err, "max_abs_sample": "1 utterance x 800 frames (seed 7) vs oracle.torch_oracle" if err is not None else None,
+                        "tflops_algorithmic": tf, "roofline": {"bound": "tensor", "achieved": tf, "peak": pk, "unit": "TFLOP/s", "frac": tf / pk,
+                                                               "note": "algorithmic FLOPs only; the 3 bf16 passes per product are overhead"}}
+        cfg3 = run_cfg3_strong(gen, dev, world, rank, dist if world > 1 else None)
+        long_form = run_long_form(gen, dev, world, rank, dist if world > 1 else None)
 
     if rank == 0:
         launches = gen.kernel_launches(B_PER_GPU, T_FRAMES)
@@ -376,6 +567,7 @@ def main():
                     "api": "HIFIapi.generate(host mel) -> host int16"},
             "gpu_launches": launches * args.steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "fp32": fp32_rec, "cfg3_strong": cfg3, "long_form": long_form,
         }))
     if world > 1:
         dist.barrier()

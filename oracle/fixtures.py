@@ -72,6 +72,11 @@ def state_digest(state: Dict[str, torch.Tensor]) -> str:
     return h.hexdigest()
 
 
+def tensor_digest(t: torch.Tensor) -> str:
+    """sha256 of one tensor's fp32 bytes (seeded inputs are regenerated in the tests, not stored)."""
+    return hashlib.sha256(np.ascontiguousarray(t.detach().cpu().numpy().astype(np.float32)).tobytes()).hexdigest()
+
+
 def to_numpy_state(state: Dict[str, torch.Tensor]) -> Dict[str, np.ndarray]:
     return {k: v.detach().cpu().numpy() for k, v in state.items()}
 

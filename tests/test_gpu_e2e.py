@@ -390,3 +390,78 @@ def test_alternative_kernel_paths_keep_parity(env):
     res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
     assert res["fp32"][0] <= FP32_TOL, res
     assert res["bf16"][1] >= BF16_SNR_DB, res
+
+
+@pytest.mark.parametrize("rates,kernels", [((5, 2), (10, 4)), ((2, 2), (8, 4)), ((8, 2), (15, 4))])
+def test_unsupported_upsampler_shapes_fail_loudly(rates, kernels):
+    """hg_plan_create rejects ConvTranspose1d shapes whose output is not exactly rate x input (odd k - u,
+    hifi/models.py:169) or whose polyphase form needs more than L + 1 GEMM rows (k > 3u) instead of running
+    with mis-sized buffers."""
+    from oracle.common import GenConfig
+
+    cfg = GenConfig(32, rates, kernels, (3,), ((1, 3, 5),), "1")
+    m = make_generator(cfg).cuda()
+    with pytest.raises(RuntimeError, match="unsupported"):
+        m(torch.zeros(1, 80, 4, device="cuda"))
+
+
+def test_data_updates_need_invalidate_and_load_state_dict_does_not():
+    """The engine's cache key cannot see `param.data` updates (the reference's own init_weights idiom,
+    hifi/vocoder/utils.py:24-27); invalidate() re-folds, load_state_dict() invalidates by itself."""
+    g = golden("tiny_rb1")
+    m = make_generator(fx.TINY_RB1, seed=5, fold=True).cuda()
+    mel = torch.from_numpy(g["mel"]).cuda()
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        y0 = m(mel).clone()
+        m.conv_post.bias.data.add_(0.25)
+        m.invalidate()
+        y1 = m(mel).clone()
+        assert not torch.equal(y0, y1)
+        m.load_state_dict(sd0)
+        assert torch.equal(m(mel), y0)
+
+
+def test_resblock_type_follows_the_block_class_built():
+    """`resblock: 1` (int, unquoted YAML) is not == "1": the reference builds ResBlock2 (hifi/models.py:155)
+    and so must the native plan and the halo."""
+    from tts_king_b200.hifi.models import Generator, ResBlock2
+
+    h = fx.make_h(fx.TINY_RB2)
+    h["resblock"] = 1
+    h.resblock = 1
+    torch.manual_seed(3)
+    m = Generator(h)
+    assert all(isinstance(b, ResBlock2) for b in m.resblocks)
+    m.remove_weight_norm()
+    m.eval().cuda()
+    y = m(fx.synthetic_mel(1, 6, seed=2).cuda())
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    ref = torch_oracle.forward(fx.TINY_RB2, sd, fx.synthetic_mel(1, 6, seed=2))
+    assert max_abs(y.cpu().numpy(), ref.numpy()) <= FP32_TOL
+    assert m.halo_frames == parallel.halo_frames(fx.make_h(fx.TINY_RB2))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
+def test_one_process_two_gpus():
+    """one process may drive several GPUs.  Function attributes (opt-in shared memory)
+    are per device, and no entry point may leave the caller's current device changed."""
+    mel = fx.synthetic_mel(2, 40, seed=3)
+    outs = []
+    for prec in ("bf16", "fp32"):
+        m0 = make_generator(fx.V1, precision=prec).to("cuda:0")
+        m1 = make_generator(fx.V1, precision=prec).to("cuda:1")
+        torch.cuda.set_device(0)
+        with torch.no_grad():
+            y1 = m1(mel.to("cuda:1"))          # first use of every kernel on device 1 while device 0 is current
+            assert torch.cuda.current_device() == 0
+            y0 = m0(mel.to("cuda:0"))
+            y1b = m1(mel.to("cuda:1"))
+        torch.cuda.synchronize(0)
+        torch.cuda.synchronize(1)
+        assert torch.equal(y0.cpu(), y1.cpu()) and torch.equal(y1.cpu(), y1b.cpu())
+        del m1                                  # plan destruction on device 1 ...
+        import gc
+        gc.collect()
+        assert torch.cuda.current_device() == 0  # ... must not move the caller
+        outs.append(y0)

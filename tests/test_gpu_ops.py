@@ -223,3 +223,19 @@ def test_tcgen05_descriptor_selftest():
     mode = int(os.environ.get("HG_DESC_MODE", "0"))
     bad = [ln for ln in report.splitlines() if f"mode={mode} " in ln and "MISMATCH" in ln]
     assert not bad, "\n".join(bad)
+
+
+@pytest.mark.parametrize("prec", ["fp32_ffma", "fp32", "bf16"])
+@pytest.mark.parametrize("n", [1, 7, 129, 800])
+def test_conv_pre_padded_k(n, prec):
+    """conv_pre's shape (hifi/models.py:152-154: Conv1d(80, 512, 7, padding=3)) on its own: 80 input channels
+    are not a multiple of the 64-wide K chunk, so the tensor-core path zero-pads K to 128 in the operand
+    and in the packed weights.  No activation on the input (slope 1.0), as in Generator.forward :186."""
+    g = torch.Generator().manual_seed(80 + n)
+    x = torch.randn(2, 80, n, generator=g)
+    w = torch.randn(512, 80, 7, generator=g) / (80 * 7) ** 0.5
+    b = torch.randn(512, generator=g) * 0.1
+    y = run_conv1d(x, w, b, 1, 1.0, None, prec)
+    ref = ref_conv1d(x, w, b, 1, 1.0, None, prec)
+    assert not torch.isnan(y).any()
+    assert (y.double() - ref).abs().max().item() <= TOL[prec] * max(1.0, ref.abs().max().item())

@@ -131,6 +131,22 @@ def main():
         with torch.no_grad():
             return g(mel)
 
+    # ---- BASELINE.json shapes on V1 (cfg-1: 1 x 256 frames; one 800-frame utterance of cfg-2): reference
+    # outputs at the sizes the bench runs.  Mels are regenerated from their seed in the tests (sha256 kept
+    # here); only the waveforms are stored.
+    if "--skip-baseline-shapes" not in sys.argv:
+        g, _ = ref_generator(fx.V1)
+        blob = dict(digest_folded=np.array(fx.state_digest({k: v.clone() for k, v in g.state_dict().items()})))
+        for tag, frames in (("cfg1", 256), ("utt800", 800)):
+            mel = fx.synthetic_mel(1, frames, seed=7)
+            blob[f"{tag}.frames"] = np.array(frames)
+            blob[f"{tag}.mel_sha256"] = np.array(fx.tensor_digest(mel))
+            blob[f"{tag}.y"] = run(g, mel).numpy()
+        np.savez_compressed(os.path.join(out_dir, "v1_baseline_shapes.npz"), **blob)
+        print("v1_baseline_shapes", {k: getattr(v, "shape", None) for k, v in blob.items()})
+    if "--baseline-shapes-only" in sys.argv:
+        return
+
     # ---- full-size configs: weights are NOT stored (55 MB); their sha256 is, and tests rebuild them
     # with the same seed through the new package's Generator(h) and compare digests.
     for name, cfg in (("v1", fx.V1), ("v2_narrow", fx.V2_NARROW), ("v3_rb2", fx.V3_RB2)):

@@ -57,6 +57,31 @@ static int fail(int code, const char* fmt, ...) {
     if (_e != cudaSuccess) return fail(HG_ECUDA, "%s: %s", #expr, cudaGetErrorString(_e));   \
   } while (0)
 
+// Every entry point that touches a device runs with that device current and puts the caller's device
+// back on return: a process that drives several GPUs from one thread (or whose garbage collector destroys
+// a plan at an arbitrary point) must not find its current device changed behind its back.
+struct DeviceScope {
+  int prev = -1;
+  bool changed = false;
+  cudaError_t err;
+  explicit DeviceScope(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) {
+      err = cudaSetDevice(dev);
+      changed = err == cudaSuccess;
+    }
+  }
+  ~DeviceScope() {
+    if (changed) cudaSetDevice(prev);
+  }
+  DeviceScope(const DeviceScope&) = delete;
+  DeviceScope& operator=(const DeviceScope&) = delete;
+};
+#define DEVICE_SCOPE(dev)                                                                                  \
+  DeviceScope _device_scope(dev);                                                                          \
+  if (_device_scope.err != cudaSuccess)                                                                    \
+  return fail(HG_ECUDA, "cudaSetDevice(%d): %s", static_cast<int>(dev), cudaGetErrorString(_device_scope.err))
+
 extern "C" int hg_abi_version(void) { return HG_ABI_VERSION; }
 extern "C" const char* hg_last_error(void) { return g_err.c_str(); }
 
@@ -107,11 +132,7 @@ static EncodeTiledFn get_encode() {
 static int make_operand_map(HgPlan* plan, const void* ptr, int L, int B, int cpitch, int kc, int box_rows,
                             CUtensorMap* out) {
   MapKey key(ptr, L, B, cpitch, kc, box_rows);
-  {
-    std::lock_guard<std::mutex> g(plan->mu);
-    auto it = plan->maps.find(key);
-    if (it != plan->maps.end()) { *out = it->second; return HG_OK; }
-  }
+  if (plan->maps.get(key, out)) return HG_OK;
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(HG_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(cpitch), static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(B)};
@@ -125,11 +146,7 @@ static int make_operand_map(HgPlan* plan, const void* ptr, int L, int B, int cpi
   if (r != CUDA_SUCCESS)
     return fail(HG_ECUDA, "cuTensorMapEncodeTiled failed (%d) for L=%d B=%d C=%d kc=%d box=%d", static_cast<int>(r), L,
                 B, cpitch, kc, box_rows);
-  {
-    std::lock_guard<std::mutex> g(plan->mu);
-    if (plan->maps.size() > 4096) plan->maps.clear();
-    plan->maps[key] = m;
-  }
+  plan->maps.put(key, m);
   *out = m;
   return HG_OK;
 }
@@ -140,11 +157,7 @@ static int make_operand_map(HgPlan* plan, const void* ptr, int L, int B, int cpi
 //   kind 2: bf16, 16 columns,  32B swizzle  (conv_tc operand copies out)
 static int make_tile_map(HgPlan* plan, const void* ptr, int L, int B, int c, int kind, CUtensorMap* out) {
   MapKey key(ptr, L, B, c, -(kind + 1), 32);
-  {
-    std::lock_guard<std::mutex> g(plan->mu);
-    auto it = plan->maps.find(key);
-    if (it != plan->maps.end()) { *out = it->second; return HG_OK; }
-  }
+  if (plan->maps.get(key, out)) return HG_OK;
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(HG_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
   const int esz = kind == 2 ? 2 : 4;
@@ -159,10 +172,7 @@ static int make_tile_map(HgPlan* plan, const void* ptr, int L, int B, int c, int
                    kind == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : kind == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(HG_ECUDA, "cuTensorMapEncodeTiled (tile kind %d) failed (%d)", kind, static_cast<int>(r));
-  {
-    std::lock_guard<std::mutex> g(plan->mu);
-    plan->maps[key] = m;
-  }
+  plan->maps.put(key, m);
   *out = m;
   return HG_OK;
 }
@@ -170,11 +180,7 @@ static int make_tile_map(HgPlan* plan, const void* ptr, int L, int B, int c, int
 // rows is one CTA's half of a weight tile in the CTA-pair kernel (no TMA swizzle: bytes land as packed)
 static int make_weight_map(HgPlan* plan, const void* ptr, long long rows, int box_rows, CUtensorMap* out) {
   MapKey key(ptr, static_cast<int>(rows), 0, 64, -10, box_rows);
-  {
-    std::lock_guard<std::mutex> g(plan->mu);
-    auto it = plan->maps.find(key);
-    if (it != plan->maps.end()) { *out = it->second; return HG_OK; }
-  }
+  if (plan->maps.get(key, out)) return HG_OK;
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(HG_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[2] = {64, static_cast<cuuint64_t>(rows)};
@@ -186,10 +192,7 @@ static int make_weight_map(HgPlan* plan, const void* ptr, long long rows, int bo
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(HG_ECUDA, "cuTensorMapEncodeTiled (weights) failed (%d)", static_cast<int>(r));
-  {
-    std::lock_guard<std::mutex> g(plan->mu);
-    plan->maps[key] = m;
-  }
+  plan->maps.put(key, m);
   *out = m;
   return HG_OK;
 }
@@ -281,9 +284,14 @@ extern "C" int hg_plan_create(const HgConfig* cfg, int device, HgPlan** out) {
   const int uic = cfg->upsample_initial_channel;
   p->layers.push_back(make_conv("conv_pre", cfg->num_mels, uic, 7, 1));
   for (int i = 0; i < cfg->num_upsamples; ++i) {
-    if (cfg->upsample_kernel_sizes[i] < cfg->upsample_rates[i]) {
+    // The schedule assumes every stage is exactly rate x longer than its input (hifi/models.py:169 pads
+    // (k - u) // 2, which gives L*u only for even k - u) and that the polyphase GEMM needs L + 1 rows
+    // (true for k <= 3u).  Anything else is rejected here rather than silently mis-sized downstream.
+    const int u = cfg->upsample_rates[i], k = cfg->upsample_kernel_sizes[i];
+    if (u < 1 || k < u || ((k - u) & 1) || k > 3 * u || (k + u - 1) / u > kMaxTaps) {
       delete p;
-      return fail(HG_EINVAL, "upsample kernel < rate is not supported");
+      return fail(HG_EINVAL, "upsampler %d: (kernel %d, rate %d) unsupported — need rate >= 1, rate <= kernel <= 3*rate, "
+                  "kernel - rate even (output length = rate x input length)", i, k, u);
     }
     p->layers.push_back(make_convT("ups." + std::to_string(i), uic >> i, uic >> (i + 1),
                                    cfg->upsample_kernel_sizes[i], cfg->upsample_rates[i]));
@@ -419,7 +427,7 @@ extern "C" int hg_plan_upload_weight(HgPlan* plan, const char* name, const float
     return fail(HG_EINVAL, "size mismatch for %s.weight: expected [%lld,%lld,%lld]", name,
                 static_cast<long long>(want[0]), static_cast<long long>(want[1]), static_cast<long long>(want[2]));
   if (bias_len != l.cout) return fail(HG_EINVAL, "size mismatch for %s.bias: expected [%d]", name, l.cout);
-  CUDA_TRY(cudaSetDevice(plan->device));
+  DEVICE_SCOPE(plan->device);
   if (l.loaded) free_layer(l);
   return pack_layer(l, weight, bias);
 }
@@ -434,7 +442,7 @@ extern "C" int hg_plan_finalize(HgPlan* plan) {
 
 extern "C" int hg_plan_destroy(HgPlan* plan) {
   if (!plan) return HG_OK;
-  cudaSetDevice(plan->device);
+  DeviceScope scope(plan->device);
   for (auto& l : plan->layers) free_layer(l);
   delete plan;
   return HG_OK;
@@ -954,7 +962,7 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
   if ((rc = layout_workspace(plan, B, T, precision, workspace, &ws))) return rc;
   if (workspace_bytes < ws.bytes)
     return fail(HG_ENOMEM, "workspace too small: %zu < %zu bytes", workspace_bytes, ws.bytes);
-  CUDA_TRY(cudaSetDevice(plan->device));
+  DEVICE_SCOPE(plan->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const HgConfig& c = plan->cfg;
   const int fmt = a_fmt_of(precision);
@@ -1081,12 +1089,9 @@ extern "C" int hg_enable_peer_access(int device, int peer_device) {
   int can = 0;
   CUDA_TRY(cudaDeviceCanAccessPeer(&can, device, peer_device));
   if (!can) return fail(HG_ENODEVICE, "device %d cannot access device %d's memory (no NVLink / PCIe peer path)", device, peer_device);
-  int prev = 0;
-  CUDA_TRY(cudaGetDevice(&prev));
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_SCOPE(device);
   cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
   if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
-  cudaSetDevice(prev);
   if (e != cudaSuccess) return fail(HG_ECUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", device, peer_device, cudaGetErrorString(e));
   return HG_OK;
 }
@@ -1122,7 +1127,7 @@ extern "C" int hg_ipc_import(int device, const unsigned char* handle64, int64_t 
   if (rc) return rc;
   // opened with `device` current: the mapping is made for THIS device's kernels, with peer access to
   // the owner enabled lazily (a mapping opened under the owner's device is not reachable from here)
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_SCOPE(device);
   cudaIpcMemHandle_t h;
   memcpy(&h, handle64, 64);
   void* b = nullptr;
@@ -1136,7 +1141,7 @@ extern "C" int hg_ipc_close(int device, void* base) {
   if (!base) return HG_OK;
   int rc = check_device(device);
   if (rc) return rc;
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_SCOPE(device);
   CUDA_TRY(cudaIpcCloseMemHandle(base));
   return HG_OK;
 }
@@ -1247,7 +1252,7 @@ extern "C" int hg_stack_forward(HgPlan* plan, const float* x, int64_t sB, int64_
   StackWorkspace ws;
   layout_stack(plan, B, T, precision, workspace, &ws);
   if (workspace_bytes < ws.bytes) return fail(HG_ENOMEM, "workspace too small: %zu < %zu bytes", workspace_bytes, ws.bytes);
-  CUDA_TRY(cudaSetDevice(plan->device));
+  DEVICE_SCOPE(plan->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int fmt = a_fmt_of(precision);
   const int n = static_cast<int>(plan->layers.size());
@@ -1361,7 +1366,7 @@ static int op_layer(int device, int precision, Layer& l, const float* x, int B, 
   int rc = check_device(device);
   if (rc) return rc;
   if (precision < HG_PREC_BF16 || precision > HG_PREC_FP32_FFMA) return fail(HG_EINVAL, "unknown precision");
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_SCOPE(device);
   HgPlan plan;
   plan.device = device;
   plan.desc_mode = env_int("HG_DESC_MODE", 0);
@@ -1380,8 +1385,8 @@ static int op_layer(int device, int precision, Layer& l, const float* x, int B, 
   const int fmt = a_fmt_of(precision);
   const bool tc = use_tc(&plan, l, precision);
   const int pitch = tc ? l.cin_pad : l.cin;
-  if (pitch != l.cin) { free_layer(l); return fail(HG_EINVAL, "op-level entry needs C_in %% 32 == 0 on the tensor-core path"); }
-  const long long n = static_cast<long long>(B) * L * l.cin;
+  // pitch > C_in: the tensor-core path zero-pads K to a multiple of 64 (conv_pre: 80 mel bins -> 128)
+  const long long n = static_cast<long long>(B) * L * pitch;
   void* a = nullptr;
   const size_t plane = align_up(static_cast<size_t>(n) * 2, 1024);
   cudaError_t e = cudaMalloc(&a, fmt == A_F32 ? static_cast<size_t>(n) * 4 : 2 * plane);
@@ -1389,7 +1394,11 @@ static int op_layer(int device, int precision, Layer& l, const float* x, int B, 
   OperandBuf in;
   in.a0 = a;
   in.a1 = fmt == A_BF16_SPLIT ? static_cast<uint8_t*>(a) + plane : nullptr;
-  e = launch_f32_to_operand(x, n, in_slope, fmt, in.a0, in.a1, st);
+  if (pitch == l.cin)
+    e = launch_f32_to_operand(x, n, in_slope, fmt, in.a0, in.a1, st);
+  else  // the strided repack the generator uses for the mel: x is [B][L][C_in] channels-last
+    e = launch_mel_to_operand(x, static_cast<long long>(L) * l.cin, 1, l.cin, B, l.cin, L, pitch, fmt, in.a0, in.a1, st,
+                              in_slope == 1.f ? 0 : 1, in_slope);
   EpiParams ep; memset(&ep, 0, sizeof(ep));
   ep.res = residual; ep.out_x = y; ep.slope = 1.f;
   rc = e == cudaSuccess ? run_layer(&plan, l, precision, B, L, in, ep, st) : fail(HG_ECUDA, "f32_to_operand: %s", cudaGetErrorString(e));
@@ -1425,7 +1434,7 @@ extern "C" int hg_op_conv_post(int device, const float* x, int B, int L, int C, 
   if (!x || !weight || !bias || !y) return fail(HG_EINVAL, "null argument");
   int rc = check_device(device);
   if (rc) return rc;
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_SCOPE(device);
   Layer l;
   l.name = "op.conv_post"; l.kind = L_POST; l.cin = C; l.cout = 1; l.k = 7; l.pad = 3;
   if ((rc = pack_layer(l, weight, bias))) { free_layer(l); return rc; }
@@ -1446,7 +1455,7 @@ extern "C" int hg_op_conv_pair(int device, const float* x, int B, int L, int C, 
   if (B < 1 || L < 1 || k < 1 || k > kMaxTaps || d1 < 1) return fail(HG_EINVAL, "bad shape");
   int rc = check_device(device);
   if (rc) return rc;
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_SCOPE(device);
   HgPlan plan;
   plan.device = device;
   plan.desc_mode = env_int("HG_DESC_MODE", 0);
@@ -1485,6 +1494,6 @@ extern "C" int hg_selftest_tcgen05(int device, char* buf, size_t buf_len) {
   if (buf && buf_len) buf[0] = 0;
   int rc = check_device(device);
   if (rc) return rc;
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_SCOPE(device);
   return run_tcgen05_selftest(buf, buf_len);
 }

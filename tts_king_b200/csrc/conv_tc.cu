@@ -18,6 +18,8 @@
 // Warp roles (608 threads): 0 weight producer | 1 MMA issuer + TMEM owner | 2 slab producer |
 // 3..18 epilogue (TMEM lane quarter = warp % 4; four warps per quarter split the column chunks).
 #include <cuda.h>
+
+#include <atomic>
 #include <cuda_bf16.h>
 #include <stdio.h>
 
@@ -452,11 +454,16 @@ template <int N_T, int KC, int MS, bool SPLIT, bool DBG = false>
 static cudaError_t launch_one(const CUtensorMap* maps, const TcConvParams& p, int n_blocks, size_t smem, int grid_ctas,
                               cudaStream_t st) {
   auto kern = conv_tc_kernel<N_T, KC, MS, SPLIT, DBG>;
-  static size_t configured = 0;  // per-instantiation high-water mark
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  // cudaFuncSetAttribute is per device: opt every device this instantiation runs on into the full
+  // 227 KB once (bit d of the mask = done for device d; setting it twice from two threads is harmless)
+  static std::atomic<unsigned long long> configured{0};
+  int dev = 0;
+  cudaError_t ed = cudaGetDevice(&dev);
+  if (ed != cudaSuccess) return ed;
+  if (dev >= 64 || !((configured.load(std::memory_order_acquire) >> dev) & 1ull)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    configured = smem;
+    if (dev < 64) configured.fetch_or(1ull << dev, std::memory_order_release);
   }
   (void)n_blocks;
   cudaLaunchConfig_t cfg = {};

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <list>
 #include <map>
 #include <mutex>
 #include <string>
@@ -48,6 +49,48 @@ struct TcTiling {
 
 using MapKey = std::tuple<const void*, int, int, int, int, int>;  // ptr, L, B, cpitch, kc, box_rows
 
+// Bounded least-recently-used cache of encoded TMA descriptors.  Keys hold raw pointers (workspace
+// and caller tensors), so a server whose requests vary in T or whose output tensors are freshly
+// allocated keeps producing new keys: the oldest entries fall out one at a time, the hot ones (the
+// current shapes, the static weight maps) stay.
+class TensorMapCache {
+ public:
+  explicit TensorMapCache(size_t capacity = 2048) : cap_(capacity) {}
+  bool get(const MapKey& k, CUtensorMap* out) {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = map_.find(k);
+    if (it == map_.end()) return false;
+    order_.splice(order_.begin(), order_, it->second.second);  // most recently used first
+    *out = it->second.first;
+    return true;
+  }
+  void put(const MapKey& k, const CUtensorMap& m) {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = map_.find(k);
+    if (it != map_.end()) {
+      it->second.first = m;
+      order_.splice(order_.begin(), order_, it->second.second);
+      return;
+    }
+    order_.push_front(k);
+    map_.emplace(k, std::make_pair(m, order_.begin()));
+    while (map_.size() > cap_) {
+      map_.erase(order_.back());
+      order_.pop_back();
+    }
+  }
+  size_t size() {
+    std::lock_guard<std::mutex> g(mu_);
+    return map_.size();
+  }
+
+ private:
+  size_t cap_;
+  std::mutex mu_;
+  std::list<MapKey> order_;
+  std::map<MapKey, std::pair<CUtensorMap, std::list<MapKey>::iterator>> map_;
+};
+
 }  // namespace hg
 
 struct HgPlan {
@@ -69,6 +112,5 @@ struct HgPlan {
   bool is_stack = false;
   std::vector<int> stack_act;
   std::vector<float> stack_slope;
-  std::mutex mu;
-  std::map<hg::MapKey, CUtensorMap> maps;
+  hg::TensorMapCache maps;
 };

@@ -33,6 +33,23 @@ class MelLinear(nn.Linear):
         self._engine: Optional[_StackEngine] = None
         self._engine_key = None
 
+    def invalidate(self):
+        """Drop the packed device weights (rebuilt on the next forward); call after a ``.data`` update."""
+        if self._engine is not None:
+            self._engine.close()
+        self._engine = None
+        self._engine_key = None
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate()
+        return out
+
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_engine"] = None

@@ -137,6 +137,25 @@ class PostNet(nn.Module):
         """``postnet(x) + x`` (fastspeech2.py:104) with the add in the last conv's epilogue."""
         return self._run(x, residual=True)
 
+    def invalidate(self):
+        """Drop the packed device weights (rebuilt on the next forward).  Needed after an update through
+        ``param.data`` / ``buffer.data``, which does not bump the tensor version the cache key watches;
+        ``load_state_dict`` and ``.to()`` call it themselves."""
+        if self._engine is not None:
+            self._engine.close()
+        self._engine = None
+        self._engine_key = None
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate()
+        return out
+
     # ------------------------------------------------------------------ internals
     def __getstate__(self):
         state = self.__dict__.copy()

@@ -256,6 +256,9 @@ class Generator(nn.Module):
         uic = h.upsample_initial_channel
         self.conv_pre = weight_norm(Conv1d(NUM_MELS, uic, 7, 1, padding=3))
         block = ResBlock1 if h.resblock == "1" else ResBlock2
+        # everything downstream (native plan, halo) follows the block class actually built: an unquoted
+        # YAML `resblock: 1` is the int 1, which the reference's `== "1"` (hifi/models.py:155) sends to ResBlock2
+        self._hp.resblock = "1" if block is ResBlock1 else "2"
 
         self.ups = nn.ModuleList()
         for i, (u, k) in enumerate(zip(h.upsample_rates, h.upsample_kernel_sizes)):
@@ -293,6 +296,29 @@ class Generator(nn.Module):
         return self._run(x, _native.OUT_F32, 1.0)
 
     # ------------------------------------------------------------------ extensions
+    def invalidate(self):
+        """Drop the packed device weights; the next forward re-folds and re-uploads them.  The engine is
+        rebuilt automatically when a parameter is replaced or updated through autograd-visible in-place ops
+        (``load_state_dict``, ``.to()``, ``remove_weight_norm``), but an update through ``param.data`` — the
+        reference's own ``init_weights`` idiom (hifi/vocoder/utils.py:24-27), EMA swaps — does not bump the
+        tensor version and cannot be seen: call this after such an update."""
+        if self._engine is not None:
+            self._engine.close()
+        self._engine = None
+        self._engine_key = None
+
+    refresh_weights = invalidate
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate()
+        return out
+
     @torch.no_grad()
     def generate_int16(self, x, max_wav_value: float = 32768.0, frames: Optional[Sequence[int]] = None):
         """forward + ``* MAX_WAV_VALUE`` + numpy-style truncating int16 cast, fused into the last
