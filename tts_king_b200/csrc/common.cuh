@@ -418,6 +418,46 @@ struct TcPairParams {
   EpiParams epi;       // epilogue of c2
 };
 
+// ------------------------------------------------------------------ fused ResBlock pair, time-folded (tcgen05)
+// conv_pair_fold.cu: the same pair as TcPairParams, with F = 128 / C consecutive (dilation-strided) time
+// rows folded into the N dimension of every MMA, so that one A-operand fetch feeds N = 128 columns.
+// One MMA group ("op") = one A start (phase slab + row shift) against a run of consecutive taps stacked
+// along N; the host lays the schedule out (api.cu::fold_schedule) and the kernel just walks it.
+constexpr int kFoldMaxOps = 24;  // k + F - 1 <= 15 + 8
+struct FoldOp {
+  int a_off16;  // A start: (bytes >> 4) from the operand buffer base (phase slab + row shift)
+  int b_blk;    // first tap (weight block) of B
+  int nblk;     // taps stacked along N: N = nblk * C
+  int d_col;    // first accumulator column
+  int rel;      // streamed weights: the oldest held weight block has had its last use after this op
+};
+struct TcFoldParams {
+  int B;
+  int L;               // sequence length (rows per item), a multiple of F
+  int r_out;           // output rows per tile (a multiple of F * d1)
+  int tiles_per_item;  // ceil(L / r_out)
+  int total_work;
+  int k, d1;
+  int delta;           // tile origin: xt row 0 of tile t is global row t * r_out - delta
+  int fdiv;            // F * d1: rows per block group of the de-interleaved input slab
+  int blk_off;         // first slab block = origin / fdiv + blk_off (<= 0)
+  int nblk_item;       // ceil(L / fdiv): extent of the block dimension of the input map
+  int nb_slab;         // blocks per slab box
+  int slab_phase_bytes, xt_phase_bytes;  // one phase slab of the input / of xt (multiples of 1024)
+  int t_bufs;          // 1 or 2 xt buffers
+  int stages;          // weight ring depth (== 2*k when w_resident)
+  int w_resident;
+  int n_ops1, n_ops2;
+  FoldOp ops1[kFoldMaxOps];  // conv 1 (dilation d1): A from the input slab
+  FoldOp ops2[kFoldMaxOps];  // conv 2 (dilation 1):  A from the xt buffer
+  const uint8_t* w1;   // packed swizzled tiles [tap][C rows][C]  (the Layer's w_hi)
+  const uint8_t* w2;
+  const float* bias1;  // [C]
+  float slope;
+  RaggedPrefix rag;
+  EpiParams epi;       // epilogue of c2 over the FOLDED view [L/F][128] (bias replicated F times)
+};
+
 // ------------------------------------------------------------------ CUDA-core (FFMA) conv
 struct FfmaConvParams {
   int B, L_in, rows, cin, n_total;
