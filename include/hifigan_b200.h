@@ -280,6 +280,31 @@ HG_API int hg_profile_forward(HgPlan* plan, const float* mel, int64_t sB, int64_
                               int* layer_index, float* layer_ms, int max_launches, int* n_launches);
 
 /*
+ * Host-only diagnostic (no device needed): the tiling and MMA schedule the time-folded ResBlock-pair
+ * kernel (csrc/conv_pair_fold.cu) uses for a pair of C -> C convs with k taps, first-conv dilation d1, on
+ * sequences of L rows — the two convs of one iteration of ResBlock1.forward (reference hifi/models.py:88-95).
+ * fusable = 0 when the shape is not covered (the N = C pair kernel or two launches run instead).
+ * ops[i] = {A phase slab, first A row, first tap of B, taps stacked along N, first accumulator column,
+ * weight block released}.  tests/test_host.py replays the whole dataflow from this description in numpy
+ * against a direct convolution.
+ */
+typedef struct HgFoldInfo {
+  int32_t fusable;
+  int32_t f;                 /* time rows folded into N: 128 / C */
+  int32_t r_out;             /* output rows per tile */
+  int32_t delta;             /* tile t covers xt rows [t*r_out - delta, ...) */
+  int32_t fdiv;              /* f * d1: rows per block group of the de-interleaved input */
+  int32_t blk_off;           /* first block group of a tile's slab, relative to its origin (<= 0) */
+  int32_t nb_slab;           /* block groups per slab */
+  int32_t slab_phase_bytes, xt_phase_bytes;
+  int32_t t_bufs, stages, weights_resident, smem_bytes;
+  int32_t n_ops1, n_ops2;
+  int32_t ops1[24][6];
+  int32_t ops2[24][6];
+} HgFoldInfo;
+HG_API int hg_fold_info(int C, int k, int d1, int L, HgFoldInfo* info);
+
+/*
  * Debug / bring-up: runs the tcgen05 descriptor self-test (shifted-row UMMA descriptors against a
  * CUDA-core reference) and writes a report into `buf`.  Returns the number of failing cases.
  */

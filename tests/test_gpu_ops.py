@@ -183,11 +183,13 @@ def test_resblock1_block_level(prec):
 
 
 @pytest.mark.parametrize("C,k,d1", [(64, 3, 1), (64, 7, 3), (64, 11, 5), (32, 3, 5), (32, 7, 1), (32, 11, 5)])
-@pytest.mark.parametrize("n", [1, 100, 246, 247, 502, 503, 1500])
+@pytest.mark.parametrize("n", [1, 100, 246, 247, 502, 503, 1500, 4, 240, 244, 248, 460, 480, 484, 496, 500, 1996, 4100])
 def test_fused_pair_parity(C, k, d1, n):
-    """The fused ResBlock-pair kernel (conv_pair_tc.cu) against the fp64 restatement of
-    hifi/models.py:90-94 with the kernel's operand model (bf16 operands, bf16 intermediate);
-    lengths straddle the 246/502-row output tiles."""
+    """The fused ResBlock-pair kernels against the fp64 restatement of hifi/models.py:90-94 with the
+    kernels' operand model (bf16 operands, bf16 intermediate).  Lengths that are a multiple of F = 128 / C
+    run the time-folded kernel (conv_pair_fold.cu; output tiles of 230..246 rows at C = 64, 460..496 at
+    C = 32, and a zeroed tail inside the last F*d1-row block group unless F*d1 divides the length), the
+    others the N = C kernel (conv_pair_tc.cu, 246/502-row tiles); both are straddled."""
     L = _native.lib()
     g = torch.Generator().manual_seed(C * 1000 + k * 10 + d1 + n)
     B = 2

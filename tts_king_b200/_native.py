@@ -38,6 +38,13 @@ class HgLayerInfo(ctypes.Structure):
         "stages", "smem_bytes", "weights_resident", "slab_buffers", "kernel_path")]
 
 
+class HgFoldInfo(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "fusable", "f", "r_out", "delta", "fdiv", "blk_off", "nb_slab", "slab_phase_bytes", "xt_phase_bytes", "t_bufs",
+        "stages", "weights_resident", "smem_bytes", "n_ops1", "n_ops2")] + [
+        ("ops1", (ctypes.c_int32 * 6) * 24), ("ops2", (ctypes.c_int32 * 6) * 24)]
+
+
 KERNEL_PATHS = {0: "cuda-core", 1: "tcgen05", 2: "tcgen05 cta_group::2", 3: "tcgen05 fused pair", 4: "cuda-core narrow",
                 5: "conv_post", 6: "repack"}
 
@@ -95,6 +102,8 @@ def lib() -> ctypes.CDLL:
     L.hg_op_conv_post.argtypes = [i, vp, i, i, i, vp, vp, vp, vp]
     L.hg_selftest_tcgen05.argtypes = [i, ctypes.c_char_p, sz]
     L.hg_op_conv_pair.argtypes = [i, vp, i, i, i, i, i, vp, vp, vp, vp, f, vp, vp, vp]
+    L.hg_fold_info.argtypes = [i, i, i, i, ctypes.POINTER(HgFoldInfo)]
+    L.hg_fold_info.restype = i
     L.hg_layer_count.argtypes = [vp, ctypes.POINTER(i)]
     L.hg_layer_info.argtypes = [vp, i, i, ctypes.POINTER(HgLayerInfo)]
     L.hg_profile_launch_info.argtypes = [vp, i, ctypes.POINTER(HgLayerInfo)]

@@ -34,6 +34,9 @@ cudaError_t launch_conv_tc2(int n_t, int ms, const CUtensorMap* maps, const TcCo
                             cudaStream_t st);
 cudaError_t launch_conv_pair_tc(int c, const CUtensorMap& m, const CUtensorMap& mr, const TcPairParams& p, size_t smem,
                                 int grid, cudaStream_t st);
+size_t conv_fold_smem_bytes(int c, int slab_phase_bytes, int xt_phase_bytes, int t_bufs, int stages, int e2_mode);
+cudaError_t launch_conv_pair_fold(int c, const CUtensorMap& m, const CUtensorMap& mr, const TcFoldParams& p, size_t smem,
+                                  int grid, cudaStream_t st);
 }  // namespace hg
 
 using namespace hg;
@@ -197,6 +200,36 @@ static int make_weight_map(HgPlan* plan, const void* ptr, long long rows, int bo
   return HG_OK;
 }
 
+// De-interleaved input slab of the time-folded pair kernel (conv_pair_fold.cu): the bf16 operand plane
+// [B][L][C] seen as [B][blk][phase][r][C] with time row = (blk*F + phase)*d + r.  One box = nb block
+// groups of one phase = nb*d consecutive shared-memory rows.  Block groups outside [0, ceil(L/(F*d)))
+// read as zero; rows >= L inside the last group are inside this map's extent and are zeroed by the kernel.
+static int make_fold_slab_map(HgPlan* plan, const void* ptr, int L, int B, int c, int d, int nb, CUtensorMap* out) {
+  MapKey key(ptr, L, B, c, -(100 + d), nb);
+  if (plan->maps.get(key, out)) return HG_OK;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(HG_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  const int f = 128 / c;
+  const cuuint64_t rowb = static_cast<cuuint64_t>(c) * 2;
+  const cuuint64_t nblk = (static_cast<cuuint64_t>(L) + static_cast<cuuint64_t>(f) * d - 1) / (static_cast<cuuint64_t>(f) * d);
+  cuuint64_t dims[5] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(f), nblk,
+                        static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[4] = {rowb, rowb * d, rowb * d * f, rowb * static_cast<cuuint64_t>(L)};
+  cuuint32_t box[5] = {static_cast<cuuint32_t>(c), static_cast<cuuint32_t>(d), 1, static_cast<cuuint32_t>(nb), 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(HG_ECUDA, "cuTensorMapEncodeTiled (folded slab) failed (%d) for L=%d B=%d C=%d d=%d nb=%d", static_cast<int>(r), L, B,
+                c, d, nb);
+  plan->maps.put(key, m);
+  *out = m;
+  return HG_OK;
+}
+
 static int make_f32_tile_map(HgPlan* plan, const void* ptr, int L, int B, int c, CUtensorMap* out) {
   return make_tile_map(plan, ptr, L, B, c, 0, out);
 }
@@ -261,6 +294,7 @@ static void init_plan_env(HgPlan* p, int device) {
   p->force_ffma = env_int("HG_FORCE_FFMA", 0) != 0;
   p->ctas_per_sm = env_int("HG_TC_CTAS_PER_SM", 1);
   p->fuse_pairs = env_int("HG_FUSE_PAIRS", 1) != 0;
+  p->fold_pairs = env_int("HG_FOLD", 1) != 0;
   p->epi_tma = env_int("HG_EPI_TMA", 1) != 0;
   p->use_tc2 = env_int("HG_TC2", 1) != 0;
 }
@@ -357,8 +391,8 @@ static int upload(const void* host, size_t bytes, void** dev) {
 }
 
 static void free_layer(Layer& l) {
-  cudaFree(l.w_hi); cudaFree(l.w_lo); cudaFree(l.w_ffma); cudaFree(l.bias); cudaFree(l.w_post);
-  l.w_hi = l.w_lo = nullptr; l.w_ffma = nullptr; l.bias = nullptr; l.w_post = nullptr;
+  cudaFree(l.w_hi); cudaFree(l.w_lo); cudaFree(l.w_ffma); cudaFree(l.bias); cudaFree(l.w_post); cudaFree(l.bias_fold);
+  l.w_hi = l.w_lo = nullptr; l.w_ffma = nullptr; l.bias = nullptr; l.w_post = nullptr; l.bias_fold = nullptr;
   l.loaded = false;
 }
 
@@ -377,6 +411,12 @@ static int pack_layer(Layer& l, const float* W, const float* bias) {
   std::vector<float> bfull(l.n_total);
   for (int n = 0; n < l.n_total; ++n) bfull[n] = bias[n % l.cout];
   if ((rc = upload(bfull.data(), bfull.size() * 4, reinterpret_cast<void**>(&l.bias)))) return rc;
+  if (l.kind == L_CONV && (l.cout == 32 || l.cout == 64)) {
+    // the time-folded pair kernel's epilogue sees F = 128 / C output rows as one 128-column row
+    std::vector<float> bf(128);
+    for (int n = 0; n < 128; ++n) bf[n] = bias[n % l.cout];
+    if ((rc = upload(bf.data(), bf.size() * 4, reinterpret_cast<void**>(&l.bias_fold)))) return rc;
+  }
   {  // CUDA-core layout [tap][cin][n_total]
     std::vector<float> wf(static_cast<size_t>(l.ntaps) * l.cin * l.n_total);
     for (int t = 0; t < l.ntaps; ++t)
@@ -861,6 +901,162 @@ static int run_pair(HgPlan* plan, const Layer& l1, const Layer& l2, const PairTi
 }
 
 // ------------------------------------------------------------------------------------------------
+// the same pair with F = 128 / C time rows folded into N (conv_pair_fold.cu)
+struct FoldTiling {
+  int f = 0, c_half = 0, smin = 0, smax = 0, nb_slab = 0, slab_phase_bytes = 0, xt_phase_bytes = 0, delta = 0, r_out = 0, fdiv = 0;
+  int t_bufs = 1, stages = 0, e2_mode = 0;
+  bool resident = false;
+  size_t smem = 0;
+};
+
+// pure geometry (no device state): also what hg_fold_info reports, so the CPU tests can replay the dataflow
+static int fold_e2_mode() { return std::min(2, std::max(0, env_int("HG_FOLD_E2", 0))); }
+
+static bool fold_geometry(int c, int k, int d1, int L, FoldTiling* t) {
+  const int e2 = fold_e2_mode();
+  t->e2_mode = e2;
+  if (c != 32 && c != 64) return false;
+  const int f = 128 / c;
+  if ((k & 1) == 0 || k > kMaxTaps || k < f || k + f - 1 > kFoldMaxOps) return false;
+  if (L < 1 || L % f != 0 || d1 < 1 || d1 > 16) return false;
+  const int rowb = c * 2, align = 1024 / rowb;
+  const int ch = (k - 1) / 2;             // taps each side
+  const int s0 = (ch + f - 1) / f;        // block-group shifts reach -s0 .. smax
+  t->f = f; t->c_half = ch; t->smin = -s0; t->smax = (f - 1 + ch) / f;
+  const int nblk_t = (128 + d1 - 1) / d1;  // block groups one 128-row M tile spans
+  t->nb_slab = nblk_t + t->smax - t->smin;
+  if (t->nb_slab > 256) return false;
+  t->slab_phase_bytes = (t->nb_slab * d1 + align - 1) / align * align * rowb;
+  t->fdiv = f * d1;
+  const int xv = (128 / d1) * d1 * f;                 // xt rows of a tile that are complete block groups
+  t->delta = t->fdiv * ((s0 + d1 - 1) / d1);           // first kept output row, a multiple of fdiv >= f*s0
+  t->r_out = (xv - ch - t->delta) / t->fdiv * t->fdiv;
+  if (t->r_out < 64) return false;
+  const int tau_max = t->fdiv * (127 / d1) + (f - 1) * d1 + 127 % d1;  // last xt row E1 writes
+  const int idx_r = t->delta / f + 127 + t->smax;                      // last xt row (per phase) G2 reads
+  const int xt_rows = std::max(tau_max / f, idx_r) + 1;
+  t->xt_phase_bytes = (xt_rows + align - 1) / align * align * rowb;
+  const size_t kMaxSmem = 227 * 1024;
+  const int all = 2 * k;
+  t->stages = 0;
+  for (int tb : {2, 1}) {
+    if (conv_fold_smem_bytes(c, t->slab_phase_bytes, t->xt_phase_bytes, tb, all, e2) <= kMaxSmem) {
+      t->resident = true; t->stages = all; t->t_bufs = tb;
+      break;
+    }
+  }
+  if (!t->stages) {
+    t->resident = false;
+    t->t_bufs = 1;
+    int s = all - 1;
+    while (s >= f + 2 && conv_fold_smem_bytes(c, t->slab_phase_bytes, t->xt_phase_bytes, 1, s, e2) > kMaxSmem) --s;
+    if (s < f + 2) return false;
+    t->stages = s;
+  }
+  t->smem = conv_fold_smem_bytes(c, t->slab_phase_bytes, t->xt_phase_bytes, t->t_bufs, t->stages, e2);
+  return true;
+}
+
+static bool fold_fusable(const HgPlan* plan, const Layer& l1, const Layer& l2, int precision, int L, FoldTiling* t) {
+  if (!plan->fuse_pairs || !plan->fold_pairs || precision != HG_PREC_BF16 || plan->force_ffma) return false;
+  if (l1.kind != L_CONV || l2.kind != L_CONV || !l1.tc || !l2.tc || !l2.bias_fold) return false;
+  const int c = l1.cin;
+  if (l1.cout != c || l2.cin != c || l2.cout != c || l1.k != l2.k || l2.dil != 1) return false;
+  return fold_geometry(c, l1.k, l1.dil, L, t);
+}
+
+// MMA groups of one conv of the folded pair.  Phase h of output M row i is time row (relative to the row
+// the M tile starts at) F*d*blk + h*d + r; tap j reads input row that + (j - ch)*d, i.e. phase
+// u = h + j - ch of the de-interleaved operand.  For every u the phases that use it form a run, and their
+// taps j = u + ch - h a run of consecutive taps: one MMA group.  Accumulator column block q = phase F-1-q,
+// so the run ascends in tap index.  Groups run in ascending u: every output element then accumulates its
+// taps in the order 0..k-1 whatever its phase (position-independent, bit-identical to conv_pair_tc.cu), and
+// the streamed weight blocks are consumed in ascending order.  The first groups cover only some phases,
+// so the kernel clears the accumulator with a zero-operand MMA instead of an overwrite flag.
+static int fold_schedule(int c, int f, int k, int row_bytes_shift16, int phase_bytes, int first_row, int rows_per_shift,
+                         FoldOp* ops) {
+  const int ch = (k - 1) / 2;
+  int n = 0;
+  for (int u = -ch; u <= f - 1 + ch; ++u) {
+    const int s = u >= 0 ? u / f : -((-u + f - 1) / f);  // floor(u / f)
+    const int hp = u - s * f;
+    const int h_lo = std::max(0, u + ch - (k - 1)), h_hi = std::min(f - 1, u + ch);
+    FoldOp& op = ops[n++];
+    op.a_off16 = (hp * phase_bytes >> 4) + (first_row + s * rows_per_shift) * row_bytes_shift16;
+    op.b_blk = u + ch - h_hi;
+    op.nblk = h_hi - h_lo + 1;
+    op.d_col = (f - 1 - h_hi) * c;
+    // tap j has its last use (phase f-1) in the group u = j - ch + f - 1
+    op.rel = (u + ch - f + 1 >= 0 && u + ch - f + 1 <= k - 1) ? 1 : 0;
+  }
+  return n;
+}
+
+static int run_pair_fold(HgPlan* plan, const Layer& l1, const Layer& l2, const FoldTiling& t, int B, int L,
+                         const OperandBuf& in, EpiParams epi, float slope, cudaStream_t st) {
+  const int c = l1.cin, f = t.f, rowb = c * 2;
+  epi.bias = l2.bias_fold;
+  epi.a_fmt = A_BF16;
+  epi.out_batch_stride = static_cast<long long>(L) * c;
+  epi.out_extent = static_cast<long long>(L) * c;
+  epi.out_row_stride = 128;  // the folded view [L/F][128]
+  epi.out_offset = 0;
+  TcFoldParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.L = L; p.r_out = t.r_out;
+  p.tiles_per_item = (L + t.r_out - 1) / t.r_out;
+  RaggedItems rag_store;
+  p.total_work = ragged_fill(&p.rag, ragged_items(&rag_store, B, L, 0), B, L, t.r_out);
+  p.k = l1.k; p.d1 = l1.dil;
+  p.delta = t.delta; p.fdiv = t.fdiv; p.blk_off = t.smin;
+  p.nblk_item = (L + t.fdiv - 1) / t.fdiv;
+  p.nb_slab = t.nb_slab;
+  p.slab_phase_bytes = t.slab_phase_bytes; p.xt_phase_bytes = t.xt_phase_bytes;
+  p.t_bufs = t.t_bufs; p.stages = t.stages; p.w_resident = t.resident ? 1 : 0;
+  // conv 1: block-group shift s = s*d1 slab rows, slab row 0 = block group (origin/fdiv + smin)
+  p.n_ops1 = fold_schedule(c, f, l1.k, rowb >> 4, t.slab_phase_bytes, -t.smin * l1.dil, l1.dil, p.ops1);
+  // conv 2 (dilation 1 over xt): M row i is output row origin + delta + F*i (+ phase), xt phase row delta/F + i + s
+  p.n_ops2 = fold_schedule(c, f, l1.k, rowb >> 4, t.xt_phase_bytes, t.delta / f, 1, p.ops2);
+  p.w1 = l1.w_hi; p.w2 = l2.w_hi; p.bias1 = l1.bias; p.slope = slope;
+  if (!epi.res) return fail(HG_ESTATE, "internal: fused pair without a residual");
+  CUtensorMap m, mr;
+  int rc = make_fold_slab_map(plan, in.a0, L, B, c, l1.dil, t.nb_slab, &m);
+  if (rc) return rc;
+  mr = m;
+  p.e2_mode = t.e2_mode;
+  if (t.e2_mode != 1) {
+    if ((rc = make_f32_tile_map(plan, epi.res, L / f, B, 128, &mr))) return rc;
+    epi.res = nullptr;  // the kernel adds the residual from its TMA-loaded tile
+  }
+  p.epi = epi;
+  const int grid = std::min(p.total_work, plan->sm_count);
+  static long long* dbg_buf = nullptr;
+  const char* dbg_layer = getenv("HG_TC_DEBUG_TIMING");  // layer name (the pair's c2) to instrument (bring-up only)
+  if (dbg_layer && l2.name == dbg_layer) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 256 * 16 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 256 * 16 * sizeof(long long), st);
+    p.dbg = dbg_buf;
+  }
+  cudaError_t e = launch_conv_pair_fold(c, m, mr, p, t.smem, grid, st);
+  if (p.dbg && e == cudaSuccess) {
+    std::vector<long long> h(256 * 16);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), dbg_buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    double s[16] = {0};
+    for (int i = 0; i < grid; ++i)
+      for (int j = 0; j < 16; ++j) s[j] += static_cast<double>(h[i * 16 + j]) / grid;
+    fprintf(stderr,
+            "[hg dbg] %s fold pair C=%d k=%d d=%d e2=%d grid=%d tiles/cta=%.1f r_out=%d resident=%d stages=%d t_bufs=%d | MMA warp: total=%.0f wait weights=%.0f "
+            "d1_empty=%.0f slab=%.0f t_full=%.0f d2_empty=%.0f | epi warp 0: total=%.0f wait d1_full=%.0f t_empty=%.0f d2_full=%.0f res=%.0f; busy E1=%.0f E2=%.0f\n",
+            l2.name.c_str(), c, p.k, p.d1, p.e2_mode, grid, s[6], p.r_out, p.w_resident, p.stages, p.t_bufs, s[0], s[1], s[2], s[3], s[4], s[5], s[8],
+            s[9], s[10], s[11], s[12], s[13], s[14]);
+  }
+  if (e != cudaSuccess) return fail(HG_ECUDA, "conv_pair_fold launch (%s): %s", l2.name.c_str(), cudaGetErrorString(e));
+  if (g_prof) prof_mark(static_cast<int>(&l2 - plan->layers.data()), make_rec(HG_PATH_FUSED_PAIR, 128, c, 1, t.stages, 2, t.resident, t.smem));
+  return HG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // workspace
 struct Workspace {
   float* F[3];
@@ -904,7 +1100,7 @@ static int layout_workspace(const HgPlan* plan, int B, int T, int precision, voi
   ws->mel.a0 = p + off;
   ws->mel.a1 = precision == HG_PREC_FP32 ? p + off + mplane : nullptr;
   off += mb;
-  ws->bytes = off;
+  ws->bytes = off + 4096;  // the folded pair kernel's input map may read (and discard) a few rows past an operand buffer
   return HG_OK;
 }
 
@@ -1039,7 +1235,11 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
             }
           }
         }
-        if (fused) {
+        FoldTiling ft;
+        if (fused && fold_fusable(plan, plan->layers[li + m], l2, precision, L, &ft)) {
+          // ... with F = 128 / C time rows folded into the MMA's N dimension  (conv_pair_fold.cu)
+          if ((rc = run_pair_fold(plan, plan->layers[li + m], l2, ft, B, L, ws.A[a_conv_in], ep, slope, st))) return rc;
+        } else if (fused) {
           // c1 and c2 in one kernel; xt never leaves shared memory  (conv_pair_tc.cu)
           if ((rc = run_pair(plan, plan->layers[li + m], l2, pt, B, L, ws.A[a_conv_in], ep, slope, st))) return rc;
         } else if ((rc = run_layer(plan, l2, precision, B, L, ws.A[a_conv_in], ep, st))) {
@@ -1463,6 +1663,7 @@ extern "C" int hg_op_conv_pair(int device, const float* x, int B, int L, int C, 
     cudaDeviceProp pr;
     if (cudaGetDeviceProperties(&pr, device) == cudaSuccess) plan.sm_count = pr.multiProcessorCount;
   }
+  plan.fold_pairs = env_int("HG_FOLD", 1) != 0;
   plan.layers.push_back(make_conv("op.pair.c1", C, C, k, d1));
   plan.layers.push_back(make_conv("op.pair.c2", C, C, k, 1));
   Layer& l1 = plan.layers[0];
@@ -1473,20 +1674,51 @@ extern "C" int hg_op_conv_pair(int device, const float* x, int B, int L, int C, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long n = static_cast<long long>(B) * L * C;
   void* a = nullptr;
-  cudaError_t e = cudaMalloc(&a, static_cast<size_t>(n) * 2);
+  // + 4 KB: the folded kernel's input map covers whole block groups, up to F*d1 - 1 rows past the last item
+  cudaError_t e = cudaMalloc(&a, static_cast<size_t>(n) * 2 + 4096);
   if (e != cudaSuccess) { free_layer(l1); free_layer(l2); return fail(HG_ECUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
   OperandBuf in;
   in.a0 = a;
   e = launch_f32_to_operand(x, n, in_slope, A_BF16, in.a0, nullptr, st);
   EpiParams ep; memset(&ep, 0, sizeof(ep));
   ep.res = residual; ep.out_x = y; ep.slope = 1.f;
-  rc = e == cudaSuccess ? run_pair(&plan, l1, l2, pt, B, L, in, ep, in_slope, st)
-                        : fail(HG_ECUDA, "f32_to_operand: %s", cudaGetErrorString(e));
+  FoldTiling ft;
+  if (e != cudaSuccess) rc = fail(HG_ECUDA, "f32_to_operand: %s", cudaGetErrorString(e));
+  else if (fold_fusable(&plan, l1, l2, HG_PREC_BF16, L, &ft)) rc = run_pair_fold(&plan, l1, l2, ft, B, L, in, ep, in_slope, st);
+  else rc = run_pair(&plan, l1, l2, pt, B, L, in, ep, in_slope, st);
   cudaError_t es = cudaStreamSynchronize(st);
   cudaFree(a);
   free_layer(l1); free_layer(l2);
   if (rc) return rc;
   if (es != cudaSuccess) return fail(HG_ECUDA, "op execution failed: %s", cudaGetErrorString(es));
+  return HG_OK;
+}
+
+extern "C" int hg_fold_info(int C, int k, int d1, int L, HgFoldInfo* info) {
+  if (!info) return fail(HG_EINVAL, "null info");
+  memset(info, 0, sizeof(*info));
+  FoldTiling t;
+  if (!fold_geometry(C, k, d1, L, &t)) return HG_OK;  // fusable = 0: the N = C pair kernel (or two launches) runs instead
+  info->fusable = 1;
+  info->f = t.f; info->r_out = t.r_out; info->delta = t.delta; info->fdiv = t.fdiv; info->blk_off = t.smin;
+  info->nb_slab = t.nb_slab; info->slab_phase_bytes = t.slab_phase_bytes; info->xt_phase_bytes = t.xt_phase_bytes;
+  info->t_bufs = t.t_bufs; info->stages = t.stages; info->weights_resident = t.resident ? 1 : 0;
+  info->smem_bytes = static_cast<int32_t>(t.smem);
+  FoldOp ops[kFoldMaxOps];
+  const int rowb = C * 2;
+  for (int conv = 0; conv < 2; ++conv) {
+    const int phase_bytes = conv ? t.xt_phase_bytes : t.slab_phase_bytes;
+    const int n = conv ? fold_schedule(C, t.f, k, rowb >> 4, t.xt_phase_bytes, t.delta / t.f, 1, ops)
+                       : fold_schedule(C, t.f, k, rowb >> 4, t.slab_phase_bytes, -t.smin * d1, d1, ops);
+    (conv ? info->n_ops2 : info->n_ops1) = n;
+    for (int i = 0; i < n; ++i) {
+      int32_t* o = conv ? info->ops2[i] : info->ops1[i];
+      const int bytes = ops[i].a_off16 * 16;
+      o[0] = bytes / phase_bytes;            // phase slab of the A operand
+      o[1] = (bytes % phase_bytes) / rowb;   // first row inside it
+      o[2] = ops[i].b_blk; o[3] = ops[i].nblk; o[4] = ops[i].d_col; o[5] = ops[i].rel;
+    }
+  }
   return HG_OK;
 }
 

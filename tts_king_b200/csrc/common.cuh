@@ -237,6 +237,27 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& e, int b, long lo
   }
 }
 
+// epilogue_rows for a caller that still has to fetch the residual itself, with the summation order of the
+// pair kernels' staged epilogue: (accumulator + residual) + bias.  All residual loads are issued first.
+template <int NR>
+__device__ __forceinline__ void epilogue_rows_res_first(EpiParams e, int b, long long q0, int row_step, int n,
+                                                        float (&v)[NR][4], long long q_limit) {
+  const long long f0 = q0 * e.out_row_stride + n + e.out_offset;
+  const long long fstep = static_cast<long long>(row_step) * e.out_row_stride;
+  const float* rp = e.res + static_cast<long long>(b) * e.out_batch_stride + f0;
+  float4 r[NR];
+#pragma unroll
+  for (int i = 0; i < NR; ++i) {
+    const long long f = f0 + i * fstep;
+    const bool ok = f >= 0 && f + 4 <= e.out_extent && q0 + static_cast<long long>(i) * row_step < q_limit;
+    r[i] = ok ? *reinterpret_cast<const float4*>(rp + i * fstep) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < NR; ++i) { v[i][0] += r[i].x; v[i][1] += r[i].y; v[i][2] += r[i].z; v[i][3] += r[i].w; }
+  e.res = nullptr;
+  epilogue_rows<NR, false>(e, b, q0, row_step, n, v, q_limit);
+}
+
 // Split form of epilogue_rows for software-pipelined epilogues: epi_prefetch issues the residual
 // loads of NR rows (and computes their validity) early; epi_finish consumes them later.
 template <int NR>
@@ -454,6 +475,8 @@ struct TcFoldParams {
   const uint8_t* w2;
   const float* bias1;  // [C]
   float slope;
+  int e2_mode;         // 0 staged (TMA residual + transposing slot), 1 register transpose + direct loads, 2 hybrid
+  long long* dbg;      // optional [grid][16] cycle counters (HG_TC_DEBUG_TIMING)
   RaggedPrefix rag;
   EpiParams epi;       // epilogue of c2 over the FOLDED view [L/F][128] (bias replicated F times)
 };

@@ -25,9 +25,20 @@
 // Accumulator columns hold the phases in REVERSE order (column block q = phase F-1-q) so that the
 // stacked weight run ascends in tap index and the Layer's packed image [tap][C][C] is used as is.
 //
+// Arithmetic order: the MMA groups run in ascending u, so every output element — whatever its phase, tile or
+// position in the sequence — accumulates its taps in the order 0..k-1 (K steps inside), exactly like
+// conv_pair_tc.cu: results are bit-identical between the two kernels, between a time chunk and the
+// monolithic forward, and between batch items.  Ascending order means the first groups cover only some of
+// the phases, so they cannot carry the "overwrite" flag; instead one extra MMA with an all-zero A operand
+// (a 1 KB block whose 8-row groups alias through SBO = 0) clears the accumulator first.
+//
+// E2 needs no shared memory: the 32 x 32 accumulator item of a warp is transposed in registers (three
+// butterfly exchanges among the eight lanes that share lane & 3) into the layout in which eight lanes cover
+// one 128-byte row segment; residual loads and the x / operand stores are then plain coalesced 16-byte
+// accesses.  That frees the 64 KB the staging slots took in conv_pair_tc.cu for weight stages.
+//
 // Geometry, schedule and the input map are laid out by the host (api.cu::fold_geometry /
-// fold_schedule); everything else — pipeline, barriers, warp roles, the TMA-prefetched residual tile —
-// is conv_pair_tc.cu's.  Rows beyond the sequence end inside the last (partial) block group cannot be
+// fold_schedule); pipeline, barriers and warp roles are conv_pair_tc.cu's.  Rows beyond the sequence end inside the last (partial) block group cannot be
 // expressed as TMA out-of-bounds, so the slab producer zeroes them in shared memory for the one tile
 // per item that sees them.
 #include <cuda.h>
@@ -41,12 +52,20 @@ namespace hg {
 
 constexpr int kFoldEpiWarps = 16;
 constexpr int kFoldThreads = (3 + kFoldEpiWarps) * 32;
-constexpr int kFoldStageFloats = 32 * 32;  // per-warp residual / transpose tile: 32 rows x 32 fp32 columns
+constexpr int kFoldZeroBytes = 1024;       // all-zero A operand of the accumulator-clearing MMA
+constexpr int kFoldStageFloats = 32 * 32;  // per-warp residual tile (E2 modes 0 and 2): 32 rows x 32 fp32 columns
 
-template <int C>
+// E2M selects how E2 gets the residual in and the rows out (all three give identical bits):
+//   0  residual tile TMA-prefetched a tile ahead into a 4 KB per-warp slot, accumulator added in place, transposed
+//      read of the slot, coalesced stores (conv_pair_tc.cu's E2)
+//   1  no shared memory at all: register transpose, then plain coalesced residual loads and stores
+//   2  TMA-prefetched residual slot read row-wise into registers, register transpose, coalesced stores
+// DBG = true is the HG_TC_DEBUG_TIMING build (cycle counters around every wait).
+template <int C, int E2M, bool DBG>
 __global__ void __launch_bounds__(kFoldThreads, 1)
 conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_res,
                       const __grid_constant__ TcFoldParams p) {
+  constexpr bool STAGED = E2M != 1;
   constexpr int F = 128 / C;
   constexpr int LOG2F = (F == 2) ? 1 : (F == 4) ? 2 : 3;
   constexpr int ROWB = C * 2;
@@ -62,10 +81,11 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int slab_bytes = F * p.slab_phase_bytes;  // one slab buffer: F phase slabs
   const int t_bytes = F * p.xt_phase_bytes;       // one xt buffer:   F phase slabs
-  uint8_t* slab = smem;                           // [2][slab_bytes]
+  uint8_t* zero_a = smem;                         // [1 KB] zeros
+  uint8_t* slab = smem + kFoldZeroBytes;          // [2][slab_bytes]
   uint8_t* tbuf = slab + 2 * slab_bytes;          // [t_bufs][t_bytes]
-  float* staging = reinterpret_cast<float*>(tbuf + p.t_bufs * t_bytes);  // [16][4 KB], 1024-aligned (TMA dst)
-  uint8_t* wst = reinterpret_cast<uint8_t*>(staging + kFoldEpiWarps * kFoldStageFloats);  // [stages][WBLK]
+  float* staging = reinterpret_cast<float*>(tbuf + p.t_bufs * t_bytes);  // [16][4 KB] (STAGED), 1024-aligned (TMA dst)
+  uint8_t* wst = reinterpret_cast<uint8_t*>(staging + (STAGED ? kFoldEpiWarps * kFoldStageFloats : 0));  // [stages][WBLK]
   uint64_t* bars = reinterpret_cast<uint64_t*>(wst + p.stages * WBLK);
   uint64_t* slab_full = bars;        // [2]
   uint64_t* slab_empty = bars + 2;   // [2]
@@ -86,7 +106,12 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
                        ? (p.total_work - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
                        : 0;
 
-  if (warp == 0 && lane == 0) { prefetch_tensormap(&map_in); prefetch_tensormap(&map_res); }
+  if (warp == 0 && lane == 0) { prefetch_tensormap(&map_in); if (STAGED) prefetch_tensormap(&map_res); }
+  if (warp == 2) {  // the zero operand (generic-proxy stores, made visible to the tensor core below)
+    *reinterpret_cast<uint4*>(zero_a + lane * 32) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(zero_a + lane * 32 + 16) = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
+  }
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < 2; ++i) {
@@ -195,12 +220,24 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
     uint32_t avail_phase = 0;
     int avail_ahead = 0;  // blocks of the current conv already waited for
     bool w_seen = false;  // resident mode: every stage has been waited for once
+    // bring-up instrumentation (HG_TC_DEBUG_TIMING): cycles spent in each wait, kept in global memory
+    long long* dbg = (DBG && p.dbg) ? p.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
+    const long long c_t0 = (DBG && dbg) ? clock64() : 0;
+    auto timed_wait = [&](uint64_t* bar, uint32_t ph, int slot) {
+      if (DBG && dbg) { const long long t0 = clock64(); mbar_wait(bar, ph); if (lane == 0) dbg[slot] += clock64() - t0; }
+      else mbar_wait(bar, ph);
+    };
 
-    auto issue = [&](uint32_t acc, uint32_t a_lo, uint32_t b_lo, int n, bool first) {
+    constexpr uint32_t desc_hi_alias = (1u << 14) | (LAYOUT << 29);  // SBO = 0: every 8-row group is the same 8 rows
+    const uint32_t zero_lo = (smem_u32(zero_a) & 0x3FFFFu) >> 4;
+    auto issue = [&](uint32_t acc, uint32_t a_lo, uint32_t b_lo, int n) {
       const uint32_t idesc = idesc0 | (static_cast<uint32_t>(n >> 3) << 17);
 #pragma unroll
-      for (int ks = 0; ks < KSTEPS; ++ks)
-        umma_bf16_lohi(acc, a_lo + ks * 2, b_lo + ks * 2, desc_hi, idesc, (first && ks == 0) ? 0u : 1u);
+      for (int ks = 0; ks < KSTEPS; ++ks) umma_bf16_lohi(acc, a_lo + ks * 2, b_lo + ks * 2, desc_hi, idesc, 1u);
+    };
+    // D[128 x 128] = 0 * (the first rows of weight block `b_lo`): one K = 16 MMA, overwrite
+    auto clear_acc = [&](uint32_t acc, uint32_t b_lo) {
+      umma_bf16_lohi(acc, zero_lo, b_lo, desc_hi_alias, idesc0 | (static_cast<uint32_t>(128 >> 3) << 17), 0u);
     };
     auto run_ops = [&](const FoldOp* ops, int n_ops, uint32_t a_base_lo, uint32_t acc, int conv) {
       if (!p.w_resident) avail_ahead = 0;
@@ -209,26 +246,28 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
         if (p.w_resident) {
           const int st = conv * p.k + b_blk;
           if (!w_seen) {
-            for (int j = 0; j < nblk; ++j) mbar_wait(&w_full[st + j], 0u);
+            for (int j = 0; j < nblk; ++j) timed_wait(&w_full[st + j], 0u, 1);
             tc_fence_after();
           }
-          if (elect_one()) issue(acc + d_col, a_base_lo + a_off, wst_lo + static_cast<uint32_t>(st) * (WBLK >> 4), nblk * C, o == 0);
+          if (elect_one()) {
+            if (o == 0) clear_acc(acc, wst_lo + static_cast<uint32_t>(st) * (WBLK >> 4));
+            issue(acc + d_col, a_base_lo + a_off, wst_lo + static_cast<uint32_t>(st) * (WBLK >> 4), nblk * C);
+          }
           __syncwarp();
         } else {
           while (avail_ahead < b_blk + nblk) {
-            mbar_wait(&w_full[avail_slot], avail_phase);
+            timed_wait(&w_full[avail_slot], avail_phase, 1);
             if (++avail_slot == p.stages) { avail_slot = 0; avail_phase ^= 1; }
             ++avail_ahead;
           }
           tc_fence_after();
-          int s0 = base_slot + b_blk;
-          if (s0 >= p.stages) s0 -= p.stages;
+          const int s0 = (base_slot + b_blk) % p.stages;
           const int n1 = (s0 + nblk <= p.stages) ? nblk : p.stages - s0;  // blocks before the ring wraps
           if (elect_one()) {
-            issue(acc + d_col, a_base_lo + a_off, wst_lo + static_cast<uint32_t>(s0) * (WBLK >> 4), n1 * C, o == 0);
-            // (a wrapped run is two MMA groups; the second half starts at ring slot 0.  Its columns were
-            // never written by op 0's first group when o == 0, so it must not accumulate either.)
-            if (n1 < nblk) issue(acc + d_col + n1 * C, a_base_lo + a_off, wst_lo, (nblk - n1) * C, o == 0);
+            if (o == 0) clear_acc(acc, wst_lo + static_cast<uint32_t>(s0) * (WBLK >> 4));
+            issue(acc + d_col, a_base_lo + a_off, wst_lo + static_cast<uint32_t>(s0) * (WBLK >> 4), n1 * C);
+            // a run that wraps around the ring is two MMA groups; the second half starts at slot 0
+            if (n1 < nblk) issue(acc + d_col + n1 * C, a_base_lo + a_off, wst_lo, (nblk - n1) * C);
             if (rel) umma_commit(&w_empty[head_slot]);
           }
           __syncwarp();
@@ -243,8 +282,8 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
     auto g1 = [&](int i) {
       const int buf = i & 1;
       const uint32_t ph = (i >> 1) & 1;
-      mbar_wait(&d1_empty[buf], ph ^ 1);
-      mbar_wait(&slab_full[buf], ph);
+      timed_wait(&d1_empty[buf], ph ^ 1, 2);
+      timed_wait(&slab_full[buf], ph, 3);
       tc_fence_after();
       run_ops(p.ops1, p.n_ops1, slab_lo + static_cast<uint32_t>(buf) * (static_cast<uint32_t>(slab_bytes) >> 4),
               tmem_u + buf * ACC_COLS, 0);
@@ -256,8 +295,8 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
       const uint32_t ph = (i >> 1) & 1;
       const int tbi = p.t_bufs == 2 ? buf : 0;
       const uint32_t tph = p.t_bufs == 2 ? ph : static_cast<uint32_t>(i & 1);
-      mbar_wait(&t_full[tbi], tph);
-      mbar_wait(&d2_empty[buf], ph ^ 1);
+      timed_wait(&t_full[tbi], tph, 4);
+      timed_wait(&d2_empty[buf], ph ^ 1, 5);
       tc_fence_after();
       run_ops(p.ops2, p.n_ops2, t_lo + static_cast<uint32_t>(tbi) * (static_cast<uint32_t>(t_bytes) >> 4),
               tmem_u + (2 + buf) * ACC_COLS, 1);
@@ -270,21 +309,26 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
       g2(i);
       w_seen = true;
     }
+    if (DBG && dbg && lane == 0) { dbg[0] = clock64() - c_t0; dbg[6] = n_my; }
   } else {
     // ------------------------------------------------ epilogue warps (all 16 do E1 then E2)
     const int e = warp - 3;
     const int quarter = warp & 3;
     const int sub = e >> 2;  // 0..3: which of the four warps sharing this TMEM lane quarter
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    float* stg = staging + e * kFoldStageFloats;
-    const int c4 = lane & 7, rsub = lane >> 3;
     // E1: this thread's M row and where its F output rows of xt go (relative to the tile origin)
     const int mrow = quarter * 32 + lane;
     const int blk1 = mrow / p.d1, r1 = mrow - blk1 * p.d1;
     // E2: this warp's 32-column item; accumulator column block q holds phase F-1-q
     const int c02 = sub * 32;                                   // accumulator columns
     const int c02m = (F - 1 - c02 / C) * C + (c02 % C);         // columns of the folded output row
-    const int n2 = c02m + c4 * 4;
+    float* stg = staging + e * kFoldStageFloats;
+    long long* dbg = (DBG && p.dbg && e == 0) ? p.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
+    const long long c_t0 = (DBG && dbg) ? clock64() : 0;
+    auto timed_wait = [&](uint64_t* bar, uint32_t ph, int slot) {
+      if (DBG && dbg) { const long long t0 = clock64(); mbar_wait(bar, ph); if (lane == 0) dbg[slot] += clock64() - t0; }
+      else mbar_wait(bar, ph);
+    };
 
     // E1: D1 -> (+b1, leaky_relu, bf16) -> xt phase slabs in UMMA layout; two 16-column items per warp
     auto e1 = [&](int i) {
@@ -296,9 +340,10 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
       const uint32_t ph = (i >> 1) & 1;
       const int tbi = p.t_bufs == 2 ? buf : 0;
       const uint32_t tph = p.t_bufs == 2 ? ph : static_cast<uint32_t>(i & 1);
-      mbar_wait(&d1_full[buf], ph);
-      mbar_wait(&t_empty[tbi], tph ^ 1);  // the G2 that last read this xt buffer has retired
+      timed_wait(&d1_full[buf], ph, 9);
+      timed_wait(&t_empty[tbi], tph ^ 1, 10);  // the G2 that last read this xt buffer has retired
       tc_fence_after();
+      const long long c_s = (DBG && dbg) ? clock64() : 0;
       uint8_t* tb = tbuf + tbi * t_bytes;
       const uint32_t tmem_acc = tmem_base + buf * ACC_COLS + lane_base;
 #pragma unroll 1
@@ -338,38 +383,60 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
       fence_proxy_async();  // generic-proxy writes of xt -> visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_full[tbi]);
+      if (DBG && dbg && lane == 0) dbg[13] += clock64() - c_s;
     };
 
     // E2 on the folded view: M row i of tile t is folded output row t*r_out/F + i (F time rows x C channels =
-    // 128 fp32 = 512 contiguous bytes).  The fp32 residual tile of this warp's item is TMA-loaded into the
-    // warp's 4 KB staging slot a whole tile ahead; the accumulator row is added in place, and after the
-    // transpose 8 lanes cover one 128-byte row segment.
+    // 128 fp32 = 512 contiguous bytes); tcgen05.ld hands lane l row l of the warp's 32 x 32 item.
     auto coords = [&](int i, int& b, int& q0) {
       const int work = blockIdx.x + i * gridDim.x;
       int tile;
       decode_tile(p.rag, p.tiles_per_item, work, b, tile);
       q0 = (tile * p.r_out) >> LOG2F;
     };
-    auto prefetch_res = [&](int i) {  // lane 0 only
+    auto prefetch_res = [&](int i) {  // lane 0 only; STAGED
       int b, q0;
       coords(i, b, q0);
       mbar_arrive_expect_tx(&res_bar[e], kFoldStageFloats * 4);
       tma_load_3d(stg, &map_res, &res_bar[e], c02m, q0 + quarter * 32, b);
     };
+    // register transpose in 4-column units among the eight lanes that share lane & 3: afterwards lane l holds
+    // columns 4*(l>>2)..+3 of rows 4*ii + (l&3), ii = 0..7 (eight lanes per 128-byte row segment)
+    auto transpose_units = [&](uint32_t (&r)[32]) {
+      const int unit = lane >> 2;
+#pragma unroll
+      for (int bit = 1; bit <= 4; bit <<= 1) {
+        const bool up = (unit & bit) != 0;
+#pragma unroll
+        for (int c_lo = 0; c_lo < 8; ++c_lo) {
+          if (c_lo & bit) continue;
+          const int c_hi = c_lo | bit;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const uint32_t send = up ? r[4 * c_lo + w] : r[4 * c_hi + w];
+            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 4 * bit);
+            if (up) r[4 * c_lo + w] = recv; else r[4 * c_hi + w] = recv;
+          }
+        }
+      }
+    };
     auto e2 = [&](int i) {
       int b, q0;
       coords(i, b, q0);
       const int buf = i & 1;
-      mbar_wait(&d2_full[buf], (i >> 1) & 1);
+      timed_wait(&d2_full[buf], (i >> 1) & 1, 11);
       tc_fence_after();
-      {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (2 + buf) * ACC_COLS + lane_base + c02, r);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&d2_empty[buf]);
-        mbar_wait(&res_bar[e], i & 1);
+      const long long c_s = (DBG && dbg) ? clock64() : 0;
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + (2 + buf) * ACC_COLS + lane_base + c02, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&d2_empty[buf]);
+      const long long q_lim = static_cast<long long>(q0) + (p.r_out >> LOG2F);
+      float v[8][4];
+      if (E2M == 0) {
+        timed_wait(&res_bar[e], i & 1, 12);
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
           float4* sp = reinterpret_cast<float4*>(stg + lane * 32 + ((k4 ^ (lane & 7)) << 2));
@@ -378,29 +445,55 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
           t.z += __uint_as_float(r[4 * k4 + 2]); t.w += __uint_as_float(r[4 * k4 + 3]);
           *sp = t;
         }
-      }
-      __syncwarp();
-      float v[8][4];
+        __syncwarp();
+        const int c4 = lane & 7, rsub = lane >> 3;
 #pragma unroll
-      for (int ii = 0; ii < 8; ++ii) {
-        const int row = ii * 4 + rsub;
-        const float4 t4 = *reinterpret_cast<const float4*>(stg + row * 32 + ((c4 ^ (row & 7)) << 2));
-        v[ii][0] = t4.x; v[ii][1] = t4.y; v[ii][2] = t4.z; v[ii][3] = t4.w;
+        for (int ii = 0; ii < 8; ++ii) {
+          const int row = ii * 4 + rsub;
+          const float4 t4 = *reinterpret_cast<const float4*>(stg + row * 32 + ((c4 ^ (row & 7)) << 2));
+          v[ii][0] = t4.x; v[ii][1] = t4.y; v[ii][2] = t4.z; v[ii][3] = t4.w;
+        }
+        fence_proxy_async();  // our generic reads of the slot happen-before the next TMA write into it
+        __syncwarp();
+        if (lane == 0 && i + 1 < n_my) prefetch_res(i + 1);
+        // (accumulator + residual) + bias here; epilogue_rows<.., true> does (accumulator + bias) + residual.
+        // Both pair kernels use this order, so they stay bit-identical to each other.
+        epilogue_rows<8, false>(p.epi, b, static_cast<long long>(q0) + quarter * 32 + rsub, 4, c02m + c4 * 4, v, q_lim);
+      } else {
+        if (E2M == 2) {
+          timed_wait(&res_bar[e], i & 1, 12);
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) {
+            const float4 t = *reinterpret_cast<const float4*>(stg + lane * 32 + ((k4 ^ (lane & 7)) << 2));
+            r[4 * k4] = __float_as_uint(t.x + __uint_as_float(r[4 * k4]));
+            r[4 * k4 + 1] = __float_as_uint(t.y + __uint_as_float(r[4 * k4 + 1]));
+            r[4 * k4 + 2] = __float_as_uint(t.z + __uint_as_float(r[4 * k4 + 2]));
+            r[4 * k4 + 3] = __float_as_uint(t.w + __uint_as_float(r[4 * k4 + 3]));
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && i + 1 < n_my) prefetch_res(i + 1);
+        }
+        transpose_units(r);
+#pragma unroll
+        for (int ii = 0; ii < 8; ++ii) {
+          v[ii][0] = __uint_as_float(r[4 * ii]); v[ii][1] = __uint_as_float(r[4 * ii + 1]);
+          v[ii][2] = __uint_as_float(r[4 * ii + 2]); v[ii][3] = __uint_as_float(r[4 * ii + 3]);
+        }
+        const long long qrow = static_cast<long long>(q0) + quarter * 32 + (lane & 3);
+        const int ncol = c02m + (lane >> 2) * 4;
+        if (E2M == 2) epilogue_rows<8, false>(p.epi, b, qrow, 4, ncol, v, q_lim);
+        else epilogue_rows_res_first<8>(p.epi, b, qrow, 4, ncol, v, q_lim);
       }
-      fence_proxy_async();  // our generic reads of the slot happen-before the next TMA write into it
-      __syncwarp();
-      if (lane == 0 && i + 1 < n_my) prefetch_res(i + 1);
-      epilogue_rows<8, false>(p.epi, b, static_cast<long long>(q0) + quarter * 32 + rsub, 4, n2, v,
-                              static_cast<long long>(q0) + (p.r_out >> LOG2F));
+      if (DBG && dbg && lane == 0) dbg[14] += clock64() - c_s;
     };
-    if (n_my > 0) {
-      if (lane == 0) prefetch_res(0);
-      e1(0);
-    }
+    if (n_my > 0 && STAGED && lane == 0) prefetch_res(0);
+    if (n_my > 0) e1(0);
     for (int i = 0; i < n_my; ++i) {
       if (i + 1 < n_my) e1(i + 1);
       e2(i);
     }
+    if (DBG && dbg && lane == 0) dbg[8] = clock64() - c_t0;
   }
 
   tc_fence_before();
@@ -409,16 +502,17 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------
-size_t conv_fold_smem_bytes(int c, int slab_phase_bytes, int xt_phase_bytes, int t_bufs, int stages) {
+size_t conv_fold_smem_bytes(int c, int slab_phase_bytes, int xt_phase_bytes, int t_bufs, int stages, int e2_mode) {
   const int f = 128 / c;
-  return 1024 + 2 * static_cast<size_t>(f) * slab_phase_bytes + static_cast<size_t>(t_bufs) * f * xt_phase_bytes +
-         static_cast<size_t>(stages) * c * c * 2 + kFoldEpiWarps * kFoldStageFloats * 4 + (34 + 2 * stages) * 8 + 16;
+  return 1024 + kFoldZeroBytes + 2 * static_cast<size_t>(f) * slab_phase_bytes +
+         static_cast<size_t>(t_bufs) * f * xt_phase_bytes + (e2_mode != 1 ? kFoldEpiWarps * kFoldStageFloats * 4 : 0) +
+         static_cast<size_t>(stages) * c * c * 2 + (34 + 2 * stages) * 8 + 16;
 }
 
-template <int C>
+template <int C, int E2M, bool DBG>
 static cudaError_t launch_fold(const CUtensorMap& m, const CUtensorMap& mr, const TcFoldParams& p, size_t smem, int grid,
                                cudaStream_t st) {
-  auto kern = conv_pair_fold_kernel<C>;
+  auto kern = conv_pair_fold_kernel<C, E2M, DBG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
@@ -434,10 +528,24 @@ static cudaError_t launch_fold(const CUtensorMap& m, const CUtensorMap& mr, cons
   return cudaLaunchKernelEx(&cfg, kern, m, mr, p);
 }
 
+template <int C>
+static cudaError_t launch_fold_c(const CUtensorMap& m, const CUtensorMap& mr, const TcFoldParams& p, size_t smem, int grid,
+                                 cudaStream_t st) {
+  if (p.dbg) {
+    if (p.e2_mode == 0) return launch_fold<C, 0, true>(m, mr, p, smem, grid, st);
+    if (p.e2_mode == 1) return launch_fold<C, 1, true>(m, mr, p, smem, grid, st);
+    return launch_fold<C, 2, true>(m, mr, p, smem, grid, st);
+  }
+  if (p.e2_mode == 0) return launch_fold<C, 0, false>(m, mr, p, smem, grid, st);
+  if (p.e2_mode == 1) return launch_fold<C, 1, false>(m, mr, p, smem, grid, st);
+  return launch_fold<C, 2, false>(m, mr, p, smem, grid, st);
+}
+
+// mr: fp32 tile map over the folded residual view [B][L/F][128] (unused when p.e2_mode == 1)
 cudaError_t launch_conv_pair_fold(int c, const CUtensorMap& m, const CUtensorMap& mr, const TcFoldParams& p, size_t smem,
                                   int grid, cudaStream_t st) {
-  if (c == 64) return launch_fold<64>(m, mr, p, smem, grid, st);
-  if (c == 32) return launch_fold<32>(m, mr, p, smem, grid, st);
+  if (c == 64) return launch_fold_c<64>(m, mr, p, smem, grid, st);
+  if (c == 32) return launch_fold_c<32>(m, mr, p, smem, grid, st);
   return cudaErrorInvalidValue;
 }
 

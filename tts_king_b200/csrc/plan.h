@@ -36,6 +36,7 @@ struct Layer {
   uint8_t* w_lo = nullptr;
   float* w_ffma = nullptr;   // [tap][cin][n_total]
   float* bias = nullptr;     // [n_total] (bias[n % cout]); conv_post: host scalar below
+  float* bias_fold = nullptr;  // [128] bias[n % cout], C = 32 / 64 convs: epilogue of the time-folded pair kernel
   float* w_post = nullptr;   // conv_post: [7][C]
   std::vector<float> w_post_host;  // same, host copy (passed by value in the kernel-parameter bank when C = 32)
   float bias_post = 0.f;
@@ -104,6 +105,7 @@ struct HgPlan {
   int force_ms = 0, force_stages = 0;
   int ctas_per_sm = 1;  // persistent grid = min(work, SMs * ctas_per_sm)
   bool fuse_pairs = true;  // HG_FUSE_PAIRS=0: never use the fused ResBlock-pair kernel
+  bool fold_pairs = true;  // HG_FOLD=0: fused pairs run on conv_pair_tc.cu (N = C) instead of conv_pair_fold.cu (N = 128)
   bool epi_tma = true;     // HG_EPI_TMA=0: always use the generic (LSU) epilogue in conv_tc
   bool use_tc2 = true;     // HG_TC2=0: never use the CTA-pair (cta_group::2) kernel for the 256/128-channel convs
   bool force_ffma = false;  // HG_FORCE_FFMA=1: route every layer to the CUDA-core kernel

@@ -65,8 +65,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > HG_MBAR_TIMEOUT_NS) {
-      printf("hifigan_b200: mbarrier timeout block(%d,%d) thread %d parity %u\n", blockIdx.x, blockIdx.y,
-             threadIdx.x, parity);
+      printf("hifigan_b200: mbarrier timeout block(%d,%d) thread %d parity %u barrier@0x%x\n", blockIdx.x, blockIdx.y,
+             threadIdx.x, parity, smem_u32(bar));
       __trap();
     }
   }
