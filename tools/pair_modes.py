@@ -47,8 +47,7 @@ def one():
 def main():
     if "--one" in sys.argv:
         return one()
-    variants = [("N=C kernel (HG_FOLD=0)", {"HG_FOLD": "0"}), ("fold, E2 staged", {"HG_FOLD_E2": "0"}),
-                ("fold, E2 registers + direct loads", {"HG_FOLD_E2": "1"}), ("fold, E2 hybrid", {"HG_FOLD_E2": "2"})]
+    variants = [("N=C kernel (HG_FOLD=0)", {"HG_FOLD": "0"}), ("fold everywhere (HG_FOLD=2)", {"HG_FOLD": "2"}), ("default mix", {})]
     out = {}
     for name, env in variants:
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--one"], capture_output=True, text=True,

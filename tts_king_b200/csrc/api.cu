@@ -34,9 +34,10 @@ cudaError_t launch_conv_tc2(int n_t, int ms, const CUtensorMap* maps, const TcCo
                             cudaStream_t st);
 cudaError_t launch_conv_pair_tc(int c, const CUtensorMap& m, const CUtensorMap& mr, const TcPairParams& p, size_t smem,
                                 int grid, cudaStream_t st);
-size_t conv_fold_smem_bytes(int c, int slab_phase_bytes, int xt_phase_bytes, int t_bufs, int stages, int e2_mode);
-cudaError_t launch_conv_pair_fold(int c, const CUtensorMap& m, const CUtensorMap& mr, const TcFoldParams& p, size_t smem,
-                                  int grid, cudaStream_t st);
+size_t conv_fold_smem_bytes(int c, int slab_phase_bytes, int xt_phase_bytes, int t_bufs, int stages);
+bool conv_fold_has_kernel(int c, int k, bool ring);
+cudaError_t launch_conv_pair_fold(int c, int k, bool ring, const CUtensorMap& m, const CUtensorMap& mr, const TcFoldParams& p,
+                                  size_t smem, int grid, cudaStream_t st);
 }  // namespace hg
 
 using namespace hg;
@@ -295,6 +296,7 @@ static void init_plan_env(HgPlan* p, int device) {
   p->ctas_per_sm = env_int("HG_TC_CTAS_PER_SM", 1);
   p->fuse_pairs = env_int("HG_FUSE_PAIRS", 1) != 0;
   p->fold_pairs = env_int("HG_FOLD", 1) != 0;
+  p->fold_force = env_int("HG_FOLD", 1) == 2;
   p->epi_tma = env_int("HG_EPI_TMA", 1) != 0;
   p->use_tc2 = env_int("HG_TC2", 1) != 0;
 }
@@ -904,17 +906,14 @@ static int run_pair(HgPlan* plan, const Layer& l1, const Layer& l2, const PairTi
 // the same pair with F = 128 / C time rows folded into N (conv_pair_fold.cu)
 struct FoldTiling {
   int f = 0, c_half = 0, smin = 0, smax = 0, nb_slab = 0, slab_phase_bytes = 0, xt_phase_bytes = 0, delta = 0, r_out = 0, fdiv = 0;
-  int t_bufs = 1, stages = 0, e2_mode = 0;
+  int t_bufs = 1, stages = 0;
   bool resident = false;
   size_t smem = 0;
 };
 
 // pure geometry (no device state): also what hg_fold_info reports, so the CPU tests can replay the dataflow
-static int fold_e2_mode() { return std::min(2, std::max(0, env_int("HG_FOLD_E2", 0))); }
-
+// pure geometry (no device state): also what hg_fold_info reports, so the CPU tests can replay the dataflow
 static bool fold_geometry(int c, int k, int d1, int L, FoldTiling* t) {
-  const int e2 = fold_e2_mode();
-  t->e2_mode = e2;
   if (c != 32 && c != 64) return false;
   const int f = 128 / c;
   if ((k & 1) == 0 || k > kMaxTaps || k < f || k + f - 1 > kFoldMaxOps) return false;
@@ -936,25 +935,39 @@ static bool fold_geometry(int c, int k, int d1, int L, FoldTiling* t) {
   const int idx_r = t->delta / f + 127 + t->smax;                      // last xt row (per phase) G2 reads
   const int xt_rows = std::max(tau_max / f, idx_r) + 1;
   t->xt_phase_bytes = (xt_rows + align - 1) / align * align * rowb;
+  // preference order: resident weights (2k stages) with two xt buffers, resident with one, then a ring as deep
+  // as fits (at least F + 2 stages: a group holds F blocks while the next ones arrive)
   const size_t kMaxSmem = 227 * 1024;
-  const int all = 2 * k;
   t->stages = 0;
-  for (int tb : {2, 1}) {
-    if (conv_fold_smem_bytes(c, t->slab_phase_bytes, t->xt_phase_bytes, tb, all, e2) <= kMaxSmem) {
-      t->resident = true; t->stages = all; t->t_bufs = tb;
-      break;
+  if (conv_fold_has_kernel(c, k, false)) {
+    for (int tb : {2, 1}) {
+      if (conv_fold_smem_bytes(c, t->slab_phase_bytes, t->xt_phase_bytes, tb, 2 * k) <= kMaxSmem) {
+        t->resident = true; t->stages = 2 * k; t->t_bufs = tb;
+        break;
+      }
     }
   }
-  if (!t->stages) {
+  if (!t->stages && conv_fold_has_kernel(c, k, true)) {
     t->resident = false;
     t->t_bufs = 1;
-    int s = all - 1;
-    while (s >= f + 2 && conv_fold_smem_bytes(c, t->slab_phase_bytes, t->xt_phase_bytes, 1, s, e2) > kMaxSmem) --s;
-    if (s < f + 2) return false;
-    t->stages = s;
+    int s = 2 * k - 1;
+    while (s >= f + 2 && conv_fold_smem_bytes(c, t->slab_phase_bytes, t->xt_phase_bytes, 1, s) > kMaxSmem) --s;
+    if (s >= f + 2) t->stages = s;
   }
-  t->smem = conv_fold_smem_bytes(c, t->slab_phase_bytes, t->xt_phase_bytes, t->t_bufs, t->stages, e2);
+  if (!t->stages) return false;
+  t->smem = conv_fold_smem_bytes(c, t->slab_phase_bytes, t->xt_phase_bytes, t->t_bufs, t->stages);
   return true;
+}
+
+// Where the time-folded kernel is the faster of the two pair kernels (A/B on B200, 16 x 800 frames,
+// profiles/r2_pair_kernel_ab.md): it wins where the N = C kernel is bound by MMA operand fetch — 32 channels
+// from k = 5 up (0.40 -> 0.28 ms at k = 11) and 64 channels at k >= 9 — and loses a few percent where the pair
+// is HBM-bound (k = 3) or when the epilogue also reads the MRF running sum with plain loads (its smaller output
+// tiles mean more of those epilogues).  HG_FOLD=2 forces it wherever it applies (tests, A/B).
+static bool fold_pays(const HgPlan* plan, const Layer& l2, bool mrf_accumulate) {
+  if (plan->fold_force) return true;
+  if (l2.cin == 32) return l2.k >= 5 && !(mrf_accumulate && l2.k >= 9);
+  return l2.k >= 9 && !mrf_accumulate;
 }
 
 static bool fold_fusable(const HgPlan* plan, const Layer& l1, const Layer& l2, int precision, int L, FoldTiling* t) {
@@ -1007,50 +1020,26 @@ static int run_pair_fold(HgPlan* plan, const Layer& l1, const Layer& l2, const F
   p.tiles_per_item = (L + t.r_out - 1) / t.r_out;
   RaggedItems rag_store;
   p.total_work = ragged_fill(&p.rag, ragged_items(&rag_store, B, L, 0), B, L, t.r_out);
-  p.k = l1.k; p.d1 = l1.dil;
+  p.d1 = l1.dil;
   p.delta = t.delta; p.fdiv = t.fdiv; p.blk_off = t.smin;
   p.nblk_item = (L + t.fdiv - 1) / t.fdiv;
   p.nb_slab = t.nb_slab;
   p.slab_phase_bytes = t.slab_phase_bytes; p.xt_phase_bytes = t.xt_phase_bytes;
-  p.t_bufs = t.t_bufs; p.stages = t.stages; p.w_resident = t.resident ? 1 : 0;
-  // conv 1: block-group shift s = s*d1 slab rows, slab row 0 = block group (origin/fdiv + smin)
-  p.n_ops1 = fold_schedule(c, f, l1.k, rowb >> 4, t.slab_phase_bytes, -t.smin * l1.dil, l1.dil, p.ops1);
-  // conv 2 (dilation 1 over xt): M row i is output row origin + delta + F*i (+ phase), xt phase row delta/F + i + s
-  p.n_ops2 = fold_schedule(c, f, l1.k, rowb >> 4, t.xt_phase_bytes, t.delta / f, 1, p.ops2);
+  p.a1_row0 = -t.smin * l1.dil;  // conv 1: slab row 0 = block group (origin / fdiv + smin)
+  p.a2_row0 = t.delta / f;       // conv 2: M row i is output row origin + delta + F*i (+ phase)
+  p.t_bufs = t.t_bufs;
   p.w1 = l1.w_hi; p.w2 = l2.w_hi; p.bias1 = l1.bias; p.slope = slope;
   if (!epi.res) return fail(HG_ESTATE, "internal: fused pair without a residual");
+  (void)rowb;
+  p.stages = t.stages;
   CUtensorMap m, mr;
   int rc = make_fold_slab_map(plan, in.a0, L, B, c, l1.dil, t.nb_slab, &m);
   if (rc) return rc;
-  mr = m;
-  p.e2_mode = t.e2_mode;
-  if (t.e2_mode != 1) {
-    if ((rc = make_f32_tile_map(plan, epi.res, L / f, B, 128, &mr))) return rc;
-    epi.res = nullptr;  // the kernel adds the residual from its TMA-loaded tile
-  }
+  if ((rc = make_f32_tile_map(plan, epi.res, L / f, B, 128, &mr))) return rc;
+  epi.res = nullptr;  // the kernel adds the residual from its TMA-loaded tile
   p.epi = epi;
   const int grid = std::min(p.total_work, plan->sm_count);
-  static long long* dbg_buf = nullptr;
-  const char* dbg_layer = getenv("HG_TC_DEBUG_TIMING");  // layer name (the pair's c2) to instrument (bring-up only)
-  if (dbg_layer && l2.name == dbg_layer) {
-    if (!dbg_buf) cudaMalloc(&dbg_buf, 256 * 16 * sizeof(long long));
-    cudaMemsetAsync(dbg_buf, 0, 256 * 16 * sizeof(long long), st);
-    p.dbg = dbg_buf;
-  }
-  cudaError_t e = launch_conv_pair_fold(c, m, mr, p, t.smem, grid, st);
-  if (p.dbg && e == cudaSuccess) {
-    std::vector<long long> h(256 * 16);
-    cudaStreamSynchronize(st);
-    cudaMemcpy(h.data(), dbg_buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-    double s[16] = {0};
-    for (int i = 0; i < grid; ++i)
-      for (int j = 0; j < 16; ++j) s[j] += static_cast<double>(h[i * 16 + j]) / grid;
-    fprintf(stderr,
-            "[hg dbg] %s fold pair C=%d k=%d d=%d e2=%d grid=%d tiles/cta=%.1f r_out=%d resident=%d stages=%d t_bufs=%d | MMA warp: total=%.0f wait weights=%.0f "
-            "d1_empty=%.0f slab=%.0f t_full=%.0f d2_empty=%.0f | epi warp 0: total=%.0f wait d1_full=%.0f t_empty=%.0f d2_full=%.0f res=%.0f; busy E1=%.0f E2=%.0f\n",
-            l2.name.c_str(), c, p.k, p.d1, p.e2_mode, grid, s[6], p.r_out, p.w_resident, p.stages, p.t_bufs, s[0], s[1], s[2], s[3], s[4], s[5], s[8],
-            s[9], s[10], s[11], s[12], s[13], s[14]);
-  }
+  cudaError_t e = launch_conv_pair_fold(c, l1.k, !t.resident, m, mr, p, t.smem, grid, st);
   if (e != cudaSuccess) return fail(HG_ECUDA, "conv_pair_fold launch (%s): %s", l2.name.c_str(), cudaGetErrorString(e));
   if (g_prof) prof_mark(static_cast<int>(&l2 - plan->layers.data()), make_rec(HG_PATH_FUSED_PAIR, 128, c, 1, t.stages, 2, t.resident, t.smem));
   return HG_OK;
@@ -1236,7 +1225,7 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
           }
         }
         FoldTiling ft;
-        if (fused && fold_fusable(plan, plan->layers[li + m], l2, precision, L, &ft)) {
+        if (fused && fold_fusable(plan, plan->layers[li + m], l2, precision, L, &ft) && fold_pays(plan, l2, ep.acc_in != nullptr)) {
           // ... with F = 128 / C time rows folded into the MMA's N dimension  (conv_pair_fold.cu)
           if ((rc = run_pair_fold(plan, plan->layers[li + m], l2, ft, B, L, ws.A[a_conv_in], ep, slope, st))) return rc;
         } else if (fused) {
@@ -1663,7 +1652,7 @@ extern "C" int hg_op_conv_pair(int device, const float* x, int B, int L, int C, 
     cudaDeviceProp pr;
     if (cudaGetDeviceProperties(&pr, device) == cudaSuccess) plan.sm_count = pr.multiProcessorCount;
   }
-  plan.fold_pairs = env_int("HG_FOLD", 1) != 0;
+  plan.fold_pairs = env_int("HG_FOLD", 1) != 0;  // the op-level entry runs the folded kernel wherever it applies
   plan.layers.push_back(make_conv("op.pair.c1", C, C, k, d1));
   plan.layers.push_back(make_conv("op.pair.c2", C, C, k, 1));
   Layer& l1 = plan.layers[0];

@@ -443,7 +443,9 @@ struct TcPairParams {
 // conv_pair_fold.cu: the same pair as TcPairParams, with F = 128 / C consecutive (dilation-strided) time
 // rows folded into the N dimension of every MMA, so that one A-operand fetch feeds N = 128 columns.
 // One MMA group ("op") = one A start (phase slab + row shift) against a run of consecutive taps stacked
-// along N; the host lays the schedule out (api.cu::fold_schedule) and the kernel just walks it.
+// along N.  The kernel derives its groups at compile time (template on the tap count); FoldOp is the
+// host-side description of the same schedule (api.cu::fold_schedule -> hg_fold_info, replayed by
+// tests/test_fold_schedule.py).
 constexpr int kFoldMaxOps = 24;  // k + F - 1 <= 15 + 8
 struct FoldOp {
   int a_off16;  // A start: (bytes >> 4) from the operand buffer base (phase slab + row shift)
@@ -458,25 +460,21 @@ struct TcFoldParams {
   int r_out;           // output rows per tile (a multiple of F * d1)
   int tiles_per_item;  // ceil(L / r_out)
   int total_work;
-  int k, d1;
+  int d1;              // dilation of conv 1 (conv 2 has dilation 1; the tap count is a template parameter)
   int delta;           // tile origin: xt row 0 of tile t is global row t * r_out - delta
   int fdiv;            // F * d1: rows per block group of the de-interleaved input slab
   int blk_off;         // first slab block = origin / fdiv + blk_off (<= 0)
   int nblk_item;       // ceil(L / fdiv): extent of the block dimension of the input map
   int nb_slab;         // blocks per slab box
   int slab_phase_bytes, xt_phase_bytes;  // one phase slab of the input / of xt (multiples of 1024)
+  int a1_row0;         // conv 1: slab row of block-group shift 0 (= -blk_off * d1); shift s adds s * d1 rows
+  int a2_row0;         // conv 2: xt phase row of shift 0 for M row 0 (= delta / F); shift s adds s rows
   int t_bufs;          // 1 or 2 xt buffers
-  int stages;          // weight ring depth (== 2*k when w_resident)
-  int w_resident;
-  int n_ops1, n_ops2;
-  FoldOp ops1[kFoldMaxOps];  // conv 1 (dilation d1): A from the input slab
-  FoldOp ops2[kFoldMaxOps];  // conv 2 (dilation 1):  A from the xt buffer
+  int stages;          // streamed weights: ring depth (resident kernels hold all 2k blocks)
   const uint8_t* w1;   // packed swizzled tiles [tap][C rows][C]  (the Layer's w_hi)
   const uint8_t* w2;
   const float* bias1;  // [C]
   float slope;
-  int e2_mode;         // 0 staged (TMA residual + transposing slot), 1 register transpose + direct loads, 2 hybrid
-  long long* dbg;      // optional [grid][16] cycle counters (HG_TC_DEBUG_TIMING)
   RaggedPrefix rag;
   EpiParams epi;       // epilogue of c2 over the FOLDED view [L/F][128] (bias replicated F times)
 };

@@ -32,15 +32,27 @@
 // the phases, so they cannot carry the "overwrite" flag; instead one extra MMA with an all-zero A operand
 // (a 1 KB block whose 8-row groups alias through SBO = 0) clears the accumulator first.
 //
-// E2 needs no shared memory: the 32 x 32 accumulator item of a warp is transposed in registers (three
-// butterfly exchanges among the eight lanes that share lane & 3) into the layout in which eight lanes cover
-// one 128-byte row segment; residual loads and the x / operand stores are then plain coalesced 16-byte
-// accesses.  That frees the 64 KB the staging slots took in conv_pair_tc.cu for weight stages.
+// The MMA issuer is ONE thread running straight-line code.  With N = 128 the tensor pipe wants a new
+// MMA every 64 cycles; the first version of this kernel walked a host-built schedule table (constant-bank
+// loads, ring-slot arithmetic with a modulo, a warp-wide elect / reconverge per group) and spent ~240 cycles
+// per MMA in its own instruction stream — slower than the kernel it was meant to replace
+// (profiles/r2_fold_issue_bound.md).  So the schedule is compile-time here: the kernel is instantiated per
+// tap count K, every group's operand offsets, N and accumulator column are constants of the unrolled code.
+// Weight stages: resident weights sit at slot conv*K + tap; streamed weights (C = 64, k >= 5: 2k blocks of
+// 8 KB do not fit) go through a ring whose slot cursor is carried from group to group (one compare per
+// step, no division) — a run of taps that wraps around the ring end is issued as two MMA groups.
 //
-// Geometry, schedule and the input map are laid out by the host (api.cu::fold_geometry /
-// fold_schedule); pipeline, barriers and warp roles are conv_pair_tc.cu's.  Rows beyond the sequence end inside the last (partial) block group cannot be
-// expressed as TMA out-of-bounds, so the slab producer zeroes them in shared memory for the one tile
-// per item that sees them.
+// E2 is conv_pair_tc.cu's: the fp32 residual tile of a warp's 32 x 32 item is TMA-prefetched a whole tile
+// ahead into the warp's 4 KB slot (over the folded view), the accumulator row is added in place and the slot
+// is read back transposed so that eight lanes cover one 128-byte row segment.  Two shared-memory-free
+// variants (register transpose by butterfly shuffles, residual by direct loads with an L2 bulk prefetch, or
+// by TMA) were measured and lost 0.03-0.06 ms per launch on the HBM-bound k = 3 pairs
+// (profiles/r2_fold_issue_bound.md).
+//
+// Geometry and the input map are laid out by the host (api.cu::fold_geometry); pipeline, barriers and
+// warp roles are conv_pair_tc.cu's.  Rows beyond the sequence end inside the last (partial) block group
+// cannot be expressed as TMA out-of-bounds, so the slab producer zeroes them in shared memory for the one
+// tile per item that sees them.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdio.h>
@@ -53,29 +65,95 @@ namespace hg {
 constexpr int kFoldEpiWarps = 16;
 constexpr int kFoldThreads = (3 + kFoldEpiWarps) * 32;
 constexpr int kFoldZeroBytes = 1024;       // all-zero A operand of the accumulator-clearing MMA
-constexpr int kFoldStageFloats = 32 * 32;  // per-warp residual tile (E2 modes 0 and 2): 32 rows x 32 fp32 columns
+constexpr int kFoldStageFloats = 32 * 32;  // per-warp residual / transpose tile: 32 rows x 32 fp32 columns
 
-// E2M selects how E2 gets the residual in and the rows out (all three give identical bits):
-//   0  residual tile TMA-prefetched a tile ahead into a 4 KB per-warp slot, accumulator added in place, transposed
-//      read of the slot, coalesced stores (conv_pair_tc.cu's E2)
-//   1  no shared memory at all: register transpose, then plain coalesced residual loads and stores
-//   2  TMA-prefetched residual slot read row-wise into registers, register transpose, coalesced stores
-// DBG = true is the HG_TC_DEBUG_TIMING build (cycle counters around every wait).
-template <int C, int E2M, bool DBG>
+__host__ __device__ constexpr int fold_floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+__host__ __device__ constexpr int fold_min(int a, int b) { return a < b ? a : b; }
+__host__ __device__ constexpr int fold_max(int a, int b) { return a > b ? a : b; }
+
+// Streamed-weight ring state of the issuing thread (RING kernels).  Blocks are numbered along the conv
+// sequence G1(0) G1(1) G2(0) G1(2) ...; consecutive blocks sit in consecutive slots.
+struct FoldRing {
+  int stages;
+  int wait_slot;         // slot of the next block to wait for
+  uint32_t wait_parity;
+  int run_slot;          // slot of the first block of the current group's tap run (also the next to release)
+};
+
+// One conv of the pair, issued by a single thread.  Group oi (u = oi - CH) contracts the A operand
+// "phase u mod F, shifted by floor(u / F) block groups" against the taps u + CH - h of the phases h that
+// use it (consecutive taps, stacked along N, ascending with the accumulator column).  Group oi is the
+// first to touch weight block oi (oi < K); its run starts at block max(0, oi - F + 1), which is also the
+// block whose last use it is (oi >= F - 1).
+//   a_base16   operand buffer base (smem address >> 4)
+//   a_phase16  bytes >> 4 between phase slabs
+//   a_row0_16  (first row) * ROWB >> 4   — the slab row of shift 0
+//   a_shift16  (rows per block-group shift) * ROWB >> 4
+//   w_lo       resident: weight stage 0 of this conv; ring: stage 0 of the ring (smem address >> 4)
+template <int C, int K, bool RING>
+__device__ __forceinline__ void fold_issue_conv(uint32_t acc, uint32_t a_base16, uint32_t a_phase16, int a_row0_16,
+                                                int a_shift16, uint32_t w_lo, uint32_t zero_lo, uint64_t* w_full,
+                                                uint64_t* w_empty, FoldRing& ring, bool wait_weights) {
+  constexpr int F = 128 / C, CH = (K - 1) / 2, ROWB = C * 2, KSTEPS = C / 16, WB16 = (C * ROWB) >> 4;
+  constexpr uint32_t SBO = 8 * ROWB;
+  constexpr uint32_t LAYOUT = (C == 64) ? UMMA_LAYOUT_SW128 : (C == 32) ? UMMA_LAYOUT_SW64 : UMMA_LAYOUT_SW32;
+  constexpr uint32_t desc_hi = ((SBO >> 4) & 0x3FFFu) | (1u << 14) | (LAYOUT << 29);
+  constexpr uint32_t desc_hi_alias = (1u << 14) | (LAYOUT << 29);  // SBO = 0: every 8-row group is the same 8 rows
+  constexpr uint32_t idesc0 = umma_idesc_bf16(128, 0);
+#pragma unroll
+  for (int oi = 0; oi < K + F - 1; ++oi) {
+    const int u = oi - CH;
+    const int s = fold_floor_div(u, F), hp = u - s * F;
+    const int h_lo = fold_max(0, u + CH - (K - 1)), h_hi = fold_min(F - 1, u + CH);
+    const int b_blk = u + CH - h_hi, nblk = h_hi - h_lo + 1, d_col = (F - 1 - h_hi) * C;
+    if (oi < K) {  // block oi is first used here
+      if (RING) {
+        mbar_wait(&w_full[ring.wait_slot], ring.wait_parity);
+        if (++ring.wait_slot == ring.stages) { ring.wait_slot = 0; ring.wait_parity ^= 1; }
+        tc_fence_after();
+      } else if (wait_weights) {
+        mbar_wait(&w_full[oi], 0u);
+        tc_fence_after();
+      }
+    }
+    const uint32_t b0 = RING ? w_lo + ring.run_slot * WB16 : w_lo + b_blk * WB16;
+    if (oi == 0)  // D[128 x 128] = 0 * (first rows of weight block 0): one K = 16 MMA with the overwrite flag
+      umma_bf16_lohi(acc, zero_lo, b0, desc_hi_alias, idesc0 | (static_cast<uint32_t>(128 >> 3) << 17), 0u);
+    const uint32_t a_lo = a_base16 + hp * a_phase16 + static_cast<uint32_t>(a_row0_16 + s * a_shift16);
+    if (!RING || nblk == 1 || ring.run_slot + nblk <= ring.stages) {
+      const uint32_t idesc = idesc0 | (static_cast<uint32_t>((nblk * C) >> 3) << 17);
+#pragma unroll
+      for (int ks = 0; ks < KSTEPS; ++ks) umma_bf16_lohi(acc + d_col, a_lo + ks * 2, b0 + ks * 2, desc_hi, idesc, 1u);
+    } else {  // the run wraps around the ring end: two groups, the second from slot 0
+      const int n1 = ring.stages - ring.run_slot;
+      const uint32_t idesc1 = idesc0 | (static_cast<uint32_t>((n1 * C) >> 3) << 17);
+      const uint32_t idesc2 = idesc0 | (static_cast<uint32_t>(((nblk - n1) * C) >> 3) << 17);
+#pragma unroll
+      for (int ks = 0; ks < KSTEPS; ++ks) umma_bf16_lohi(acc + d_col, a_lo + ks * 2, b0 + ks * 2, desc_hi, idesc1, 1u);
+#pragma unroll
+      for (int ks = 0; ks < KSTEPS; ++ks) umma_bf16_lohi(acc + d_col + n1 * C, a_lo + ks * 2, w_lo + ks * 2, desc_hi, idesc2, 1u);
+    }
+    if (RING && oi >= F - 1 && oi - F + 1 <= K - 1) {  // block oi - F + 1 (= the run's first) is done
+      umma_commit(&w_empty[ring.run_slot]);
+      if (++ring.run_slot == ring.stages) ring.run_slot = 0;
+    }
+  }
+}
+
+// RING = false: all 2K weight blocks stay in shared memory (slot conv*K + tap); RING = true: p.stages slots.
+template <int C, int K, bool RING>
 __global__ void __launch_bounds__(kFoldThreads, 1)
 conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_res,
                       const __grid_constant__ TcFoldParams p) {
-  constexpr bool STAGED = E2M != 1;
   constexpr int F = 128 / C;
   constexpr int LOG2F = (F == 2) ? 1 : (F == 4) ? 2 : 3;
   constexpr int ROWB = C * 2;
-  constexpr int KSTEPS = C / 16;
   constexpr int WBLK = C * ROWB;  // one tap's [C rows][C] tile
+  const int STAGES = RING ? p.stages : 2 * K;
   constexpr uint32_t ACC_COLS = 128;
   constexpr uint32_t TMEM_COLS = 4 * ACC_COLS;
-  constexpr uint32_t SBO = 8 * ROWB;
-  constexpr uint32_t LAYOUT = (C == 64) ? UMMA_LAYOUT_SW128 : (C == 32) ? UMMA_LAYOUT_SW64 : UMMA_LAYOUT_SW32;
-  static_assert(C == 64 || C == 32, "C = 16 needs the half-swapped E2 item (see DESIGN.md)");
+  static_assert(C == 64 || C == 32, "C = 16 needs the half-swapped E2 item");
+  static_assert(K >= F && (K & 1), "every phase must be covered by one group; odd taps");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -84,9 +162,9 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
   uint8_t* zero_a = smem;                         // [1 KB] zeros
   uint8_t* slab = smem + kFoldZeroBytes;          // [2][slab_bytes]
   uint8_t* tbuf = slab + 2 * slab_bytes;          // [t_bufs][t_bytes]
-  float* staging = reinterpret_cast<float*>(tbuf + p.t_bufs * t_bytes);  // [16][4 KB] (STAGED), 1024-aligned (TMA dst)
-  uint8_t* wst = reinterpret_cast<uint8_t*>(staging + (STAGED ? kFoldEpiWarps * kFoldStageFloats : 0));  // [stages][WBLK]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wst + p.stages * WBLK);
+  float* staging = reinterpret_cast<float*>(tbuf + p.t_bufs * t_bytes);  // [16][4 KB], 1024-aligned (TMA dst)
+  uint8_t* wst = reinterpret_cast<uint8_t*>(staging + kFoldEpiWarps * kFoldStageFloats);  // [STAGES][WBLK]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wst + STAGES * WBLK);
   uint64_t* slab_full = bars;        // [2]
   uint64_t* slab_empty = bars + 2;   // [2]
   uint64_t* slab_land = bars + 4;    // [2]  TMA landing barrier of a slab that needs its tail rows zeroed
@@ -97,16 +175,16 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
   uint64_t* d2_full = bars + 14;     // [2]  G2 -> E2
   uint64_t* d2_empty = bars + 16;    // [2]  E2 -> G2
   uint64_t* res_bar = bars + 18;     // [16] residual tile landed in a warp's staging slot (TMA)
-  uint64_t* w_full = bars + 34;      // [stages]
-  uint64_t* w_empty = w_full + p.stages;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_empty + p.stages);
+  uint64_t* w_full = bars + 34;      // [STAGES]
+  uint64_t* w_empty = w_full + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_empty + STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_my = p.total_work > static_cast<int>(blockIdx.x)
                        ? (p.total_work - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
                        : 0;
 
-  if (warp == 0 && lane == 0) { prefetch_tensormap(&map_in); if (STAGED) prefetch_tensormap(&map_res); }
+  if (warp == 0 && lane == 0) { prefetch_tensormap(&map_in); prefetch_tensormap(&map_res); }
   if (warp == 2) {  // the zero operand (generic-proxy stores, made visible to the tensor core below)
     *reinterpret_cast<uint4*>(zero_a + lane * 32) = make_uint4(0u, 0u, 0u, 0u);
     *reinterpret_cast<uint4*>(zero_a + lane * 32 + 16) = make_uint4(0u, 0u, 0u, 0u);
@@ -120,7 +198,7 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
         mbar_init(&t_full[i], kFoldEpiWarps); mbar_init(&t_empty[i], 1);
         mbar_init(&d2_full[i], 1); mbar_init(&d2_empty[i], kFoldEpiWarps);
       }
-      for (int s = 0; s < p.stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
       for (int w = 0; w < kFoldEpiWarps; ++w) mbar_init(&res_bar[w], 1);
       fence_mbar_init();
     }
@@ -139,11 +217,11 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
   if (warp == 0) {
     // ------------------------------------------------ weight producer: blocks in the order the MMA issuer needs them
     if (lane == 0 && n_my > 0) {
-      if (p.w_resident) {
+      if (!RING) {
         for (int cv = 0; cv < 2; ++cv) {
           const uint8_t* w = cv ? p.w2 : p.w1;
-          for (int j = 0; j < p.k; ++j) {
-            const int st = cv * p.k + j;
+          for (int j = 0; j < K; ++j) {
+            const int st = cv * K + j;
             mbar_arrive_expect_tx(&w_full[st], WBLK);
             bulk_load_1d(wst + st * WBLK, w + static_cast<size_t>(j) * WBLK, WBLK, &w_full[st]);
           }
@@ -151,11 +229,11 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
       } else {
         int stage = 0; uint32_t phase = 0;
         auto load_conv = [&](const uint8_t* w) {
-          for (int j = 0; j < p.k; ++j) {
+          for (int j = 0; j < K; ++j) {
             mbar_wait(&w_empty[stage], phase ^ 1);
             mbar_arrive_expect_tx(&w_full[stage], WBLK);
             bulk_load_1d(wst + stage * WBLK, w + static_cast<size_t>(j) * WBLK, WBLK, &w_full[stage]);
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         };
         load_conv(p.w1);                       // G1(0)
@@ -169,7 +247,7 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
     // ------------------------------------------------ input slab producer (TMA), all lanes walk the loop
     const uint32_t box_bytes = static_cast<uint32_t>(p.nb_slab) * p.d1 * ROWB;
     const int tail = p.L - (p.nblk_item - 1) * p.fdiv;  // valid rows of the item's last block group (fdiv when full)
-    uint32_t land_uses[2] = {0, 0};
+    uint32_t land_uses0 = 0, land_uses1 = 0;
     for (int i = 0; i < n_my; ++i) {
       const int work = blockIdx.x + i * gridDim.x;
       int b, tile;
@@ -189,14 +267,15 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
       if (fix) {
         // rows L .. nblk_item*fdiv - 1 sit inside the tensor map's extent (they are the next item's first
         // rows, or whatever follows the buffer): the convolution must see zeros there
-        mbar_wait(&slab_land[buf], land_uses[buf] & 1);
-        ++land_uses[buf];
-        constexpr int CH = ROWB / 16;
-        const int nz = (p.fdiv - tail) * CH;
+        const uint32_t uses = buf ? land_uses1 : land_uses0;
+        mbar_wait(&slab_land[buf], uses & 1);
+        if (buf) ++land_uses1; else ++land_uses0;
+        constexpr int CH16 = ROWB / 16;
+        const int nz = (p.fdiv - tail) * CH16;
         for (int e = lane; e < nz; e += 32) {
-          const int o = tail + e / CH;               // row offset inside the block group
+          const int o = tail + e / CH16;             // row offset inside the block group
           const int h = o / p.d1, r = o - h * p.d1;
-          uint8_t* rp = dst + h * p.slab_phase_bytes + (last_rel * p.d1 + r) * ROWB + (e % CH) * 16;
+          uint8_t* rp = dst + h * p.slab_phase_bytes + (last_rel * p.d1 + r) * ROWB + (e % CH16) * 16;
           *reinterpret_cast<uint4*>(rp) = make_uint4(0u, 0u, 0u, 0u);
         }
         fence_proxy_async();
@@ -206,110 +285,54 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
       __syncwarp();
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc0 = umma_idesc_bf16(128, 0);
-    constexpr uint32_t desc_hi = ((SBO >> 4) & 0x3FFFu) | (1u << 14) | (LAYOUT << 29);
-    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const uint32_t slab_lo = (smem_u32(slab) & 0x3FFFFu) >> 4;
-    const uint32_t t_lo = (smem_u32(tbuf) & 0x3FFFFu) >> 4;
-    const uint32_t wst_lo = (smem_u32(wst) & 0x3FFFFu) >> 4;
-    // streamed weights: blocks are numbered along the conv sequence G1(0) G1(1) G2(0) G1(2) ...; block n sits
-    // in ring slot n % stages.  base = slot of the current conv's block 0, avail = next block to wait for,
-    // head = oldest block not yet released.
-    int base_slot = 0, avail_slot = 0, head_slot = 0;
-    uint32_t avail_phase = 0;
-    int avail_ahead = 0;  // blocks of the current conv already waited for
-    bool w_seen = false;  // resident mode: every stage has been waited for once
-    // bring-up instrumentation (HG_TC_DEBUG_TIMING): cycles spent in each wait, kept in global memory
-    long long* dbg = (DBG && p.dbg) ? p.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
-    const long long c_t0 = (DBG && dbg) ? clock64() : 0;
-    auto timed_wait = [&](uint64_t* bar, uint32_t ph, int slot) {
-      if (DBG && dbg) { const long long t0 = clock64(); mbar_wait(bar, ph); if (lane == 0) dbg[slot] += clock64() - t0; }
-      else mbar_wait(bar, ph);
-    };
-
-    constexpr uint32_t desc_hi_alias = (1u << 14) | (LAYOUT << 29);  // SBO = 0: every 8-row group is the same 8 rows
-    const uint32_t zero_lo = (smem_u32(zero_a) & 0x3FFFFu) >> 4;
-    auto issue = [&](uint32_t acc, uint32_t a_lo, uint32_t b_lo, int n) {
-      const uint32_t idesc = idesc0 | (static_cast<uint32_t>(n >> 3) << 17);
-#pragma unroll
-      for (int ks = 0; ks < KSTEPS; ++ks) umma_bf16_lohi(acc, a_lo + ks * 2, b_lo + ks * 2, desc_hi, idesc, 1u);
-    };
-    // D[128 x 128] = 0 * (the first rows of weight block `b_lo`): one K = 16 MMA, overwrite
-    auto clear_acc = [&](uint32_t acc, uint32_t b_lo) {
-      umma_bf16_lohi(acc, zero_lo, b_lo, desc_hi_alias, idesc0 | (static_cast<uint32_t>(128 >> 3) << 17), 0u);
-    };
-    auto run_ops = [&](const FoldOp* ops, int n_ops, uint32_t a_base_lo, uint32_t acc, int conv) {
-      if (!p.w_resident) avail_ahead = 0;
-      for (int o = 0; o < n_ops; ++o) {
-        const int a_off = ops[o].a_off16, b_blk = ops[o].b_blk, nblk = ops[o].nblk, d_col = ops[o].d_col, rel = ops[o].rel;
-        if (p.w_resident) {
-          const int st = conv * p.k + b_blk;
-          if (!w_seen) {
-            for (int j = 0; j < nblk; ++j) timed_wait(&w_full[st + j], 0u, 1);
-            tc_fence_after();
-          }
-          if (elect_one()) {
-            if (o == 0) clear_acc(acc, wst_lo + static_cast<uint32_t>(st) * (WBLK >> 4));
-            issue(acc + d_col, a_base_lo + a_off, wst_lo + static_cast<uint32_t>(st) * (WBLK >> 4), nblk * C);
-          }
-          __syncwarp();
-        } else {
-          while (avail_ahead < b_blk + nblk) {
-            timed_wait(&w_full[avail_slot], avail_phase, 1);
-            if (++avail_slot == p.stages) { avail_slot = 0; avail_phase ^= 1; }
-            ++avail_ahead;
-          }
-          tc_fence_after();
-          const int s0 = (base_slot + b_blk) % p.stages;
-          const int n1 = (s0 + nblk <= p.stages) ? nblk : p.stages - s0;  // blocks before the ring wraps
-          if (elect_one()) {
-            if (o == 0) clear_acc(acc, wst_lo + static_cast<uint32_t>(s0) * (WBLK >> 4));
-            issue(acc + d_col, a_base_lo + a_off, wst_lo + static_cast<uint32_t>(s0) * (WBLK >> 4), n1 * C);
-            // a run that wraps around the ring is two MMA groups; the second half starts at slot 0
-            if (n1 < nblk) issue(acc + d_col + n1 * C, a_base_lo + a_off, wst_lo, (nblk - n1) * C);
-            if (rel) umma_commit(&w_empty[head_slot]);
-          }
-          __syncwarp();
-          if (rel && ++head_slot == p.stages) head_slot = 0;
-        }
+    // ------------------------------------------------ MMA issuer: one thread, straight-line groups.  The guard is
+    // elect.sync, not `lane == 0`: only then does the compiler know a single lane is active and feed tcgen05.mma's
+    // uniform-register operands with plain R2UR moves instead of a per-instruction "waterfall" loop.
+    if (elect_one()) {
+      const uint32_t slab_lo = (smem_u32(slab) & 0x3FFFFu) >> 4;
+      const uint32_t t_lo = (smem_u32(tbuf) & 0x3FFFFu) >> 4;
+      const uint32_t wst_lo = (smem_u32(wst) & 0x3FFFFu) >> 4;
+      const uint32_t zero_lo = (smem_u32(zero_a) & 0x3FFFFu) >> 4;
+      const uint32_t slab_buf16 = static_cast<uint32_t>(slab_bytes) >> 4, t_buf16 = static_cast<uint32_t>(t_bytes) >> 4;
+      const uint32_t slab_phase16 = static_cast<uint32_t>(p.slab_phase_bytes) >> 4, xt_phase16 = static_cast<uint32_t>(p.xt_phase_bytes) >> 4;
+      const int a1_row0_16 = p.a1_row0 * (ROWB >> 4), a2_row0_16 = p.a2_row0 * (ROWB >> 4);
+      const int a1_shift16 = p.d1 * (ROWB >> 4), a2_shift16 = ROWB >> 4;
+      FoldRing ring{STAGES, 0, 0u, 0};
+      bool w_seen1 = false, w_seen2 = false;  // resident weights: waited for during the first conv 1 / conv 2 only
+      auto g1 = [&](int i) {
+        const int buf = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        mbar_wait(&d1_empty[buf], ph ^ 1);
+        mbar_wait(&slab_full[buf], ph);
+        tc_fence_after();
+        fold_issue_conv<C, K, RING>(tmem_base + buf * ACC_COLS, slab_lo + buf * slab_buf16, slab_phase16, a1_row0_16, a1_shift16,
+                                    wst_lo, zero_lo, w_full, w_empty, ring, !w_seen1);
+        umma_commit(&slab_empty[buf]);
+        umma_commit(&d1_full[buf]);
+        w_seen1 = true;
+      };
+      auto g2 = [&](int i) {
+        const int buf = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        const int tbi = p.t_bufs == 2 ? buf : 0;
+        const uint32_t tph = p.t_bufs == 2 ? ph : static_cast<uint32_t>(i & 1);
+        mbar_wait(&t_full[tbi], tph);
+        mbar_wait(&d2_empty[buf], ph ^ 1);
+        tc_fence_after();
+        fold_issue_conv<C, K, RING>(tmem_base + (2 + buf) * ACC_COLS, t_lo + tbi * t_buf16, xt_phase16, a2_row0_16, a2_shift16,
+                                    RING ? wst_lo : wst_lo + K * (WBLK >> 4), zero_lo, RING ? w_full : w_full + K,
+                                    RING ? w_empty : w_empty + K, ring, !w_seen2);
+        umma_commit(&t_empty[tbi]);
+        umma_commit(&d2_full[buf]);
+        w_seen2 = true;
+      };
+      if (n_my > 0) g1(0);
+      for (int i = 0; i < n_my; ++i) {
+        if (i + 1 < n_my) g1(i + 1);
+        g2(i);
       }
-      if (!p.w_resident) {
-        base_slot += p.k % p.stages;
-        if (base_slot >= p.stages) base_slot -= p.stages;
-      }
-    };
-    auto g1 = [&](int i) {
-      const int buf = i & 1;
-      const uint32_t ph = (i >> 1) & 1;
-      timed_wait(&d1_empty[buf], ph ^ 1, 2);
-      timed_wait(&slab_full[buf], ph, 3);
-      tc_fence_after();
-      run_ops(p.ops1, p.n_ops1, slab_lo + static_cast<uint32_t>(buf) * (static_cast<uint32_t>(slab_bytes) >> 4),
-              tmem_u + buf * ACC_COLS, 0);
-      if (elect_one()) { umma_commit(&slab_empty[buf]); umma_commit(&d1_full[buf]); }
-      __syncwarp();
-    };
-    auto g2 = [&](int i) {
-      const int buf = i & 1;
-      const uint32_t ph = (i >> 1) & 1;
-      const int tbi = p.t_bufs == 2 ? buf : 0;
-      const uint32_t tph = p.t_bufs == 2 ? ph : static_cast<uint32_t>(i & 1);
-      timed_wait(&t_full[tbi], tph, 4);
-      timed_wait(&d2_empty[buf], ph ^ 1, 5);
-      tc_fence_after();
-      run_ops(p.ops2, p.n_ops2, t_lo + static_cast<uint32_t>(tbi) * (static_cast<uint32_t>(t_bytes) >> 4),
-              tmem_u + (2 + buf) * ACC_COLS, 1);
-      if (elect_one()) { umma_commit(&t_empty[tbi]); umma_commit(&d2_full[buf]); }
-      __syncwarp();
-    };
-    if (n_my > 0) g1(0);
-    for (int i = 0; i < n_my; ++i) {
-      if (i + 1 < n_my) g1(i + 1);
-      g2(i);
-      w_seen = true;
     }
-    if (DBG && dbg && lane == 0) { dbg[0] = clock64() - c_t0; dbg[6] = n_my; }
+    __syncwarp();
   } else {
     // ------------------------------------------------ epilogue warps (all 16 do E1 then E2)
     const int e = warp - 3;
@@ -322,13 +345,6 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
     // E2: this warp's 32-column item; accumulator column block q holds phase F-1-q
     const int c02 = sub * 32;                                   // accumulator columns
     const int c02m = (F - 1 - c02 / C) * C + (c02 % C);         // columns of the folded output row
-    float* stg = staging + e * kFoldStageFloats;
-    long long* dbg = (DBG && p.dbg && e == 0) ? p.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
-    const long long c_t0 = (DBG && dbg) ? clock64() : 0;
-    auto timed_wait = [&](uint64_t* bar, uint32_t ph, int slot) {
-      if (DBG && dbg) { const long long t0 = clock64(); mbar_wait(bar, ph); if (lane == 0) dbg[slot] += clock64() - t0; }
-      else mbar_wait(bar, ph);
-    };
 
     // E1: D1 -> (+b1, leaky_relu, bf16) -> xt phase slabs in UMMA layout; two 16-column items per warp
     auto e1 = [&](int i) {
@@ -340,10 +356,9 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
       const uint32_t ph = (i >> 1) & 1;
       const int tbi = p.t_bufs == 2 ? buf : 0;
       const uint32_t tph = p.t_bufs == 2 ? ph : static_cast<uint32_t>(i & 1);
-      timed_wait(&d1_full[buf], ph, 9);
-      timed_wait(&t_empty[tbi], tph ^ 1, 10);  // the G2 that last read this xt buffer has retired
+      mbar_wait(&d1_full[buf], ph);
+      mbar_wait(&t_empty[tbi], tph ^ 1);  // the G2 that last read this xt buffer has retired
       tc_fence_after();
-      const long long c_s = (DBG && dbg) ? clock64() : 0;
       uint8_t* tb = tbuf + tbi * t_bytes;
       const uint32_t tmem_acc = tmem_base + buf * ACC_COLS + lane_base;
 #pragma unroll 1
@@ -383,60 +398,50 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
       fence_proxy_async();  // generic-proxy writes of xt -> visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_full[tbi]);
-      if (DBG && dbg && lane == 0) dbg[13] += clock64() - c_s;
     };
 
     // E2 on the folded view: M row i of tile t is folded output row t*r_out/F + i (F time rows x C channels =
-    // 128 fp32 = 512 contiguous bytes); tcgen05.ld hands lane l row l of the warp's 32 x 32 item.
+    // 128 fp32 = 512 contiguous bytes).  The fp32 residual tile of this warp's item is TMA-loaded into the
+    // warp's 4 KB staging slot (128B-swizzled box = the staging swizzle) a whole tile ahead; the accumulator
+    // row is added to it in place, and after the transpose 8 lanes cover one 128-byte row segment.
+    float* stg = staging + e * kFoldStageFloats;
+    const int c4 = lane & 7, rsub = lane >> 3;
+    const int n2 = c02m + c4 * 4;
     auto coords = [&](int i, int& b, int& q0) {
       const int work = blockIdx.x + i * gridDim.x;
       int tile;
       decode_tile(p.rag, p.tiles_per_item, work, b, tile);
       q0 = (tile * p.r_out) >> LOG2F;
     };
-    auto prefetch_res = [&](int i) {  // lane 0 only; STAGED
+    auto prefetch_res = [&](int i) {  // lane 0 only
       int b, q0;
       coords(i, b, q0);
       mbar_arrive_expect_tx(&res_bar[e], kFoldStageFloats * 4);
       tma_load_3d(stg, &map_res, &res_bar[e], c02m, q0 + quarter * 32, b);
-    };
-    // register transpose in 4-column units among the eight lanes that share lane & 3: afterwards lane l holds
-    // columns 4*(l>>2)..+3 of rows 4*ii + (l&3), ii = 0..7 (eight lanes per 128-byte row segment)
-    auto transpose_units = [&](uint32_t (&r)[32]) {
-      const int unit = lane >> 2;
-#pragma unroll
-      for (int bit = 1; bit <= 4; bit <<= 1) {
-        const bool up = (unit & bit) != 0;
-#pragma unroll
-        for (int c_lo = 0; c_lo < 8; ++c_lo) {
-          if (c_lo & bit) continue;
-          const int c_hi = c_lo | bit;
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            const uint32_t send = up ? r[4 * c_lo + w] : r[4 * c_hi + w];
-            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 4 * bit);
-            if (up) r[4 * c_lo + w] = recv; else r[4 * c_hi + w] = recv;
-          }
-        }
+      // the MRF running sum of the same tile (last pair of ResBlocks 1, 2 of a stage) is read by plain loads in
+      // epilogue_rows: pull its contiguous 64 KB block into L2 now so that they do not wait on HBM
+      if (e == 0 && p.epi.acc_in) {
+        const long long first = static_cast<long long>(q0) * 128;
+        const long long left = (p.epi.out_extent - first) * 4;
+        if (left > 0)
+          bulk_prefetch_l2(p.epi.acc_in + static_cast<long long>(b) * p.epi.out_batch_stride + first,
+                           static_cast<uint32_t>(left < 65536 ? left : 65536) & ~15u);
       }
     };
     auto e2 = [&](int i) {
       int b, q0;
       coords(i, b, q0);
       const int buf = i & 1;
-      timed_wait(&d2_full[buf], (i >> 1) & 1, 11);
+      mbar_wait(&d2_full[buf], (i >> 1) & 1);
       tc_fence_after();
-      const long long c_s = (DBG && dbg) ? clock64() : 0;
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + (2 + buf) * ACC_COLS + lane_base + c02, r);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&d2_empty[buf]);
-      const long long q_lim = static_cast<long long>(q0) + (p.r_out >> LOG2F);
-      float v[8][4];
-      if (E2M == 0) {
-        timed_wait(&res_bar[e], i & 1, 12);
+      {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (2 + buf) * ACC_COLS + lane_base + c02, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&d2_empty[buf]);
+        mbar_wait(&res_bar[e], i & 1);
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
           float4* sp = reinterpret_cast<float4*>(stg + lane * 32 + ((k4 ^ (lane & 7)) << 2));
@@ -445,55 +450,29 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
           t.z += __uint_as_float(r[4 * k4 + 2]); t.w += __uint_as_float(r[4 * k4 + 3]);
           *sp = t;
         }
-        __syncwarp();
-        const int c4 = lane & 7, rsub = lane >> 3;
-#pragma unroll
-        for (int ii = 0; ii < 8; ++ii) {
-          const int row = ii * 4 + rsub;
-          const float4 t4 = *reinterpret_cast<const float4*>(stg + row * 32 + ((c4 ^ (row & 7)) << 2));
-          v[ii][0] = t4.x; v[ii][1] = t4.y; v[ii][2] = t4.z; v[ii][3] = t4.w;
-        }
-        fence_proxy_async();  // our generic reads of the slot happen-before the next TMA write into it
-        __syncwarp();
-        if (lane == 0 && i + 1 < n_my) prefetch_res(i + 1);
-        // (accumulator + residual) + bias here; epilogue_rows<.., true> does (accumulator + bias) + residual.
-        // Both pair kernels use this order, so they stay bit-identical to each other.
-        epilogue_rows<8, false>(p.epi, b, static_cast<long long>(q0) + quarter * 32 + rsub, 4, c02m + c4 * 4, v, q_lim);
-      } else {
-        if (E2M == 2) {
-          timed_wait(&res_bar[e], i & 1, 12);
-#pragma unroll
-          for (int k4 = 0; k4 < 8; ++k4) {
-            const float4 t = *reinterpret_cast<const float4*>(stg + lane * 32 + ((k4 ^ (lane & 7)) << 2));
-            r[4 * k4] = __float_as_uint(t.x + __uint_as_float(r[4 * k4]));
-            r[4 * k4 + 1] = __float_as_uint(t.y + __uint_as_float(r[4 * k4 + 1]));
-            r[4 * k4 + 2] = __float_as_uint(t.z + __uint_as_float(r[4 * k4 + 2]));
-            r[4 * k4 + 3] = __float_as_uint(t.w + __uint_as_float(r[4 * k4 + 3]));
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0 && i + 1 < n_my) prefetch_res(i + 1);
-        }
-        transpose_units(r);
-#pragma unroll
-        for (int ii = 0; ii < 8; ++ii) {
-          v[ii][0] = __uint_as_float(r[4 * ii]); v[ii][1] = __uint_as_float(r[4 * ii + 1]);
-          v[ii][2] = __uint_as_float(r[4 * ii + 2]); v[ii][3] = __uint_as_float(r[4 * ii + 3]);
-        }
-        const long long qrow = static_cast<long long>(q0) + quarter * 32 + (lane & 3);
-        const int ncol = c02m + (lane >> 2) * 4;
-        if (E2M == 2) epilogue_rows<8, false>(p.epi, b, qrow, 4, ncol, v, q_lim);
-        else epilogue_rows_res_first<8>(p.epi, b, qrow, 4, ncol, v, q_lim);
       }
-      if (DBG && dbg && lane == 0) dbg[14] += clock64() - c_s;
+      __syncwarp();
+      float v[8][4];
+#pragma unroll
+      for (int ii = 0; ii < 8; ++ii) {
+        const int row = ii * 4 + rsub;
+        const float4 t4 = *reinterpret_cast<const float4*>(stg + row * 32 + ((c4 ^ (row & 7)) << 2));
+        v[ii][0] = t4.x; v[ii][1] = t4.y; v[ii][2] = t4.z; v[ii][3] = t4.w;
+      }
+      fence_proxy_async();  // our generic reads of the slot happen-before the next TMA write into it
+      __syncwarp();
+      if (lane == 0 && i + 1 < n_my) prefetch_res(i + 1);
+      epilogue_rows<8, false>(p.epi, b, static_cast<long long>(q0) + quarter * 32 + rsub, 4, n2, v,
+                              static_cast<long long>(q0) + (p.r_out >> LOG2F));
     };
-    if (n_my > 0 && STAGED && lane == 0) prefetch_res(0);
-    if (n_my > 0) e1(0);
+    if (n_my > 0) {
+      if (lane == 0) prefetch_res(0);
+      e1(0);
+    }
     for (int i = 0; i < n_my; ++i) {
       if (i + 1 < n_my) e1(i + 1);
       e2(i);
     }
-    if (DBG && dbg && lane == 0) dbg[8] = clock64() - c_t0;
   }
 
   tc_fence_before();
@@ -502,17 +481,26 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------
-size_t conv_fold_smem_bytes(int c, int slab_phase_bytes, int xt_phase_bytes, int t_bufs, int stages, int e2_mode) {
+// stages: 2k when resident, the ring depth otherwise
+size_t conv_fold_smem_bytes(int c, int slab_phase_bytes, int xt_phase_bytes, int t_bufs, int stages) {
   const int f = 128 / c;
   return 1024 + kFoldZeroBytes + 2 * static_cast<size_t>(f) * slab_phase_bytes +
-         static_cast<size_t>(t_bufs) * f * xt_phase_bytes + (e2_mode != 1 ? kFoldEpiWarps * kFoldStageFloats * 4 : 0) +
+         static_cast<size_t>(t_bufs) * f * xt_phase_bytes + kFoldEpiWarps * kFoldStageFloats * 4 +
          static_cast<size_t>(stages) * c * c * 2 + (34 + 2 * stages) * 8 + 16;
 }
 
-template <int C, int E2M, bool DBG>
+// (C, k, streamed?) combinations the kernel is instantiated for: C = 32 keeps its weights resident for every
+// k; C = 64 does for k = 3 and streams from k = 5 on
+bool conv_fold_has_kernel(int c, int k, bool ring) {
+  if (c == 32) return !ring && (k == 5 || k == 7 || k == 9 || k == 11);
+  if (c == 64) return ring ? (k == 5 || k == 7 || k == 9 || k == 11) : k == 3;
+  return false;
+}
+
+template <int C, int K, bool RING>
 static cudaError_t launch_fold(const CUtensorMap& m, const CUtensorMap& mr, const TcFoldParams& p, size_t smem, int grid,
                                cudaStream_t st) {
-  auto kern = conv_pair_fold_kernel<C, E2M, DBG>;
+  auto kern = conv_pair_fold_kernel<C, K, RING>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
@@ -528,24 +516,16 @@ static cudaError_t launch_fold(const CUtensorMap& m, const CUtensorMap& mr, cons
   return cudaLaunchKernelEx(&cfg, kern, m, mr, p);
 }
 
-template <int C>
-static cudaError_t launch_fold_c(const CUtensorMap& m, const CUtensorMap& mr, const TcFoldParams& p, size_t smem, int grid,
-                                 cudaStream_t st) {
-  if (p.dbg) {
-    if (p.e2_mode == 0) return launch_fold<C, 0, true>(m, mr, p, smem, grid, st);
-    if (p.e2_mode == 1) return launch_fold<C, 1, true>(m, mr, p, smem, grid, st);
-    return launch_fold<C, 2, true>(m, mr, p, smem, grid, st);
-  }
-  if (p.e2_mode == 0) return launch_fold<C, 0, false>(m, mr, p, smem, grid, st);
-  if (p.e2_mode == 1) return launch_fold<C, 1, false>(m, mr, p, smem, grid, st);
-  return launch_fold<C, 2, false>(m, mr, p, smem, grid, st);
-}
-
-// mr: fp32 tile map over the folded residual view [B][L/F][128] (unused when p.e2_mode == 1)
-cudaError_t launch_conv_pair_fold(int c, const CUtensorMap& m, const CUtensorMap& mr, const TcFoldParams& p, size_t smem,
-                                  int grid, cudaStream_t st) {
-  if (c == 64) return launch_fold_c<64>(m, mr, p, smem, grid, st);
-  if (c == 32) return launch_fold_c<32>(m, mr, p, smem, grid, st);
+// mr: fp32 tile map over the folded residual view [B][L/F][128]
+cudaError_t launch_conv_pair_fold(int c, int k, bool ring, const CUtensorMap& m, const CUtensorMap& mr, const TcFoldParams& p,
+                                  size_t smem, int grid, cudaStream_t st) {
+  if (!conv_fold_has_kernel(c, k, ring)) return cudaErrorInvalidValue;
+#define HG_FOLD_CASE(CV, KV, RV) \
+  if (c == CV && k == KV && ring == RV) return launch_fold<CV, KV, RV>(m, mr, p, smem, grid, st);
+  HG_FOLD_CASE(32, 5, false) HG_FOLD_CASE(32, 7, false) HG_FOLD_CASE(32, 9, false) HG_FOLD_CASE(32, 11, false)
+  HG_FOLD_CASE(64, 3, false)
+  HG_FOLD_CASE(64, 5, true) HG_FOLD_CASE(64, 7, true) HG_FOLD_CASE(64, 9, true) HG_FOLD_CASE(64, 11, true)
+#undef HG_FOLD_CASE
   return cudaErrorInvalidValue;
 }
 

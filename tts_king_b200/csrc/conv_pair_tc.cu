@@ -307,6 +307,17 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
       coords(i, b, m0);
       mbar_arrive_expect_tx(&res_bar[e], kPairStageFloats * 4);
       tma_load_3d(stg, &map_res, &res_bar[e], c02, m0 + ms2 * 128 + quarter * 32, b);
+      // the MRF running sum of the same tile is read by plain loads in epilogue_rows: pull its contiguous block
+      // (r_out rows x C fp32) into L2 a tile ahead so that they do not wait on HBM
+      if (e == 0 && p.epi.acc_in) {
+        const long long first = static_cast<long long>(m0) * C;
+        long long left = (p.epi.out_extent - first) * 4;
+        const long long want = static_cast<long long>(p.r_out) * C * 4;
+        if (left > want) left = want;
+        if (left > 0)
+          bulk_prefetch_l2(p.epi.acc_in + static_cast<long long>(b) * p.epi.out_batch_stride + first,
+                           static_cast<uint32_t>(left) & ~15u);
+      }
     };
     auto e2 = [&](int i) {
       int b, m0;
