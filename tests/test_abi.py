@@ -46,16 +46,18 @@ def test_struct_layout_matches_header(tmp_path):
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "hifigan_b200.h"\n'
         "int main(void) {\n"
-        '  printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(HgConfig), sizeof(HgLayerInfo), sizeof(HgStackLayer),\n'
+        '  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(HgConfig), sizeof(HgLayerInfo), sizeof(HgStackLayer),\n'
         "         offsetof(HgConfig, resblock_dilation_sizes), offsetof(HgLayerInfo, kernel_path),\n"
-        "         offsetof(HgLayerInfo, n_tile), offsetof(HgStackLayer, slope));\n"
+        "         offsetof(HgLayerInfo, n_tile), offsetof(HgStackLayer, slope), sizeof(HgFoldInfo),\n"
+        "         offsetof(HgFoldInfo, ops1), offsetof(HgFoldInfo, ops2));\n"
         "  return (HG_PATH_REPACK == 6 && HG_ACT_TANH == 2 && HG_OUT_I16 != HG_OUT_F32) ? 0 : 1;\n}\n")
     exe = tmp_path / "layout"
     subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     want = [ctypes.sizeof(_native.HgConfig), ctypes.sizeof(_native.HgLayerInfo), ctypes.sizeof(_native.HgStackLayer),
             _native.HgConfig.resblock_dilation_sizes.offset, _native.HgLayerInfo.kernel_path.offset,
-            _native.HgLayerInfo.n_tile.offset, _native.HgStackLayer.slope.offset]
+            _native.HgLayerInfo.n_tile.offset, _native.HgStackLayer.slope.offset, ctypes.sizeof(_native.HgFoldInfo),
+            _native.HgFoldInfo.ops1.offset, _native.HgFoldInfo.ops2.offset]
     assert [int(v) for v in out] == want
 
 

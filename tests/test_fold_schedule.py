@@ -125,13 +125,18 @@ CASES = [(64, 3, 1), (64, 3, 3), (64, 3, 5), (64, 7, 1), (64, 7, 3), (64, 7, 5),
          (32, 7, 1), (32, 7, 3), (32, 7, 5), (32, 11, 1), (32, 11, 3), (32, 11, 5), (32, 5, 2), (64, 5, 7)]
 
 
-@pytest.mark.parametrize("C,k,d1", CASES)
+CASES16 = [(16, 3, 1), (16, 3, 3), (16, 3, 5), (16, 7, 1), (16, 7, 3), (16, 7, 5), (16, 11, 1), (16, 11, 3), (16, 11, 5), (16, 5, 2)]
+
+
+@pytest.mark.parametrize("C,k,d1", CASES + CASES16)
 @pytest.mark.parametrize("L", [4, 236, 1000, 1204])
 def test_fold_schedule_reproduces_the_pair(C, k, d1, L):
+    L = -(-L // (128 // C)) * (128 // C)  # the folded kernel needs L % F == 0 (F = 8 at 16 channels)
     info = fold_info(C, k, d1, L)
     assert info.fusable == 1
     assert info.smem_bytes <= 227 * 1024
     assert info.stages >= (2 * k if info.weights_resident else info.f + 2)
+    assert info.weights_resident or C == 64
     rng = np.random.default_rng(C * 1000 + k * 10 + d1 + L)
     a = rng.standard_normal((L, C))
     x = rng.standard_normal((L, C))
@@ -149,6 +154,7 @@ def test_fold_schedule_reproduces_the_pair(C, k, d1, L):
 
 def test_fold_falls_back_where_it_does_not_apply():
     assert fold_info(64, 11, 1, 1001).fusable == 0   # L not a multiple of F = 2
-    assert fold_info(32, 3, 1, 1000).fusable == 0    # k < F = 4: no MMA group covers every phase
-    assert fold_info(128, 3, 1, 1000).fusable == 0   # only C = 32 / 64
+    assert fold_info(32, 3, 1, 1000).fusable == 0    # no kernel instantiated (HBM-bound on the N = C kernel anyway)
+    assert fold_info(128, 3, 1, 1000).fusable == 0   # only C = 16 / 32 / 64
+    assert fold_info(16, 7, 3, 1004).fusable == 0    # 1004 % 8 != 0
     assert fold_info(32, 11, 5, 1002).fusable == 0   # 1002 % 4 != 0

@@ -182,14 +182,18 @@ def test_resblock1_block_level(prec):
     assert err <= (2e-5 if prec == "fp32" else 5e-2) * r.abs().max().item(), err
 
 
-@pytest.mark.parametrize("C,k,d1", [(64, 3, 1), (64, 7, 3), (64, 11, 5), (32, 3, 5), (32, 7, 1), (32, 11, 5)])
-@pytest.mark.parametrize("n", [1, 100, 246, 247, 502, 503, 1500, 4, 240, 244, 248, 460, 480, 484, 496, 500, 1996, 4100])
+@pytest.mark.parametrize("C,k,d1", [(64, 3, 1), (64, 7, 3), (64, 11, 5), (32, 3, 5), (32, 7, 1), (32, 11, 5), (64, 11, 1), (32, 11, 3),
+                                    (16, 3, 1), (16, 7, 3), (16, 11, 5), (16, 3, 5), (16, 11, 1)])
+@pytest.mark.parametrize("n", [1, 100, 246, 247, 502, 503, 1500, 8, 240, 244, 248, 460, 480, 496, 920, 1000, 1996, 4104])
 def test_fused_pair_parity(C, k, d1, n):
     """The fused ResBlock-pair kernels against the fp64 restatement of hifi/models.py:90-94 with the
     kernels' operand model (bf16 operands, bf16 intermediate).  Lengths that are a multiple of F = 128 / C
     run the time-folded kernel (conv_pair_fold.cu; output tiles of 230..246 rows at C = 64, 460..496 at
-    C = 32, and a zeroed tail inside the last F*d1-row block group unless F*d1 divides the length), the
-    others the N = C kernel (conv_pair_tc.cu, 246/502-row tiles); both are straddled."""
+    C = 32, 920..1000 at C = 16, and a zeroed tail inside the last F*d1-row block group unless F*d1 divides
+    the length), the others the N = C kernel (conv_pair_tc.cu, 246/502-row tiles); both are straddled.
+    Where both kernels apply they must agree bit for bit (same summation order for every output)."""
+    if C == 16 and n % 8:
+        pytest.skip("16 channels: only the time-folded kernel exists, and it needs L % 8 == 0")
     L = _native.lib()
     g = torch.Generator().manual_seed(C * 1000 + k * 10 + d1 + n)
     B = 2
@@ -207,6 +211,18 @@ def test_fused_pair_parity(C, k, d1, n):
                                     b2.data_ptr(), 0.1, rc_.data_ptr(), y.data_ptr(),
                                     torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
+    if C != 16:
+        import os
+        y_nc = torch.full((B, n, C), float("nan"), device=dev)
+        os.environ["HG_FOLD"] = "0"
+        try:
+            _native.check(L.hg_op_conv_pair(0, xc.data_ptr(), B, n, C, k, d1, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                                            b2.data_ptr(), 0.1, rc_.data_ptr(), y_nc.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream))
+        finally:
+            del os.environ["HG_FOLD"]
+        torch.cuda.synchronize()
+        assert torch.equal(y, y_nc)
     y = y.cpu().transpose(1, 2)
     a = bf16_round(F.leaky_relu(x, 0.1))
     xt = F.conv1d(a, bf16_round(w1), b1.double(), dilation=d1, padding=(k * d1 - d1) // 2)

@@ -1,71 +1,75 @@
 #!/usr/bin/env python
-"""A/B of the fused ResBlock-pair kernels on the bench workload (16 x 800 frames, bf16): per-launch times of
-the 18 pair launches for the N = C kernel (HG_FOLD=0) and the time-folded kernel with each E2 variant
-(HG_FOLD_E2=0/1/2), plus a sha256 of the waveform (all variants must give the same bits).
+"""A/B of the fused ResBlock-pair kernels on the bench workload (16 x 800 frames, bf16), interleaved in ONE
+process so that clock / power drift hits every variant alike: three generators are built under different
+HG_FOLD settings (read at plan creation) and timed round-robin.
 
-    python tools/pair_modes.py                 # all variants, one subprocess each
-    HG_TC_DEBUG_TIMING=resblocks.8.convs2.0 python tools/pair_modes.py --one   # wait breakdown of one launch
+    N=C      HG_FOLD=0   conv_pair_tc.cu everywhere
+    fold     HG_FOLD=2   conv_pair_fold.cu wherever it applies
+    default              the shipped mix (api.cu::fold_pays)
+
+Prints whole-forward time per variant (mean of the rounds), per-launch times of the 18 pair launches (mean of
+the per-launch event passes) and the sha256 of the waveform (all variants must give the same bits).
 """
 import hashlib
-import json
 import os
-import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+import torch  # noqa: E402
 
-def one():
-    import torch
+from oracle import fixtures as fx  # noqa: E402
+from _util import make_generator  # noqa: E402
 
-    from oracle import fixtures as fx
-    from _util import make_generator
-
-    m = make_generator(fx.V1, precision="bf16").cuda()
-    mel = fx.synthetic_mel(16, 800, seed=7).cuda()
-    with torch.no_grad():
-        y = m(mel)
-        torch.cuda.synchronize()
-        digest = hashlib.sha256(y.cpu().numpy().tobytes()).hexdigest()[:16]
-        for _ in range(3):
-            m(mel)
-        rows = m.profile_layers(mel)
-        rows = m.profile_layers(mel)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(20):
-            m(mel)
-        e1.record()
-        torch.cuda.synchronize()
-    pairs = {r["name"]: round(r["ms"], 4) for r in rows if r.get("kernel") == "tcgen05 fused pair"}
-    print(json.dumps({"digest": digest, "ms_per_step": e0.elapsed_time(e1) / 20, "pair_ms_total": round(sum(pairs.values()), 3),
-                      "pairs": pairs}))
+VARIANTS = [("N=C", {"HG_FOLD": "0"}), ("fold", {"HG_FOLD": "2"}), ("default", {})]
+ROUNDS = int(os.environ.get("ROUNDS", "6"))
 
 
 def main():
-    if "--one" in sys.argv:
-        return one()
-    variants = [("N=C kernel (HG_FOLD=0)", {"HG_FOLD": "0"}), ("fold everywhere (HG_FOLD=2)", {"HG_FOLD": "2"}), ("default mix", {})]
-    out = {}
-    for name, env in variants:
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--one"], capture_output=True, text=True,
-                           env={**os.environ, **env}, timeout=600)
-        line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-        if not line:
-            print(name, "FAILED", r.stderr[-1500:])
-            continue
-        out[name] = json.loads(line[-1])
-        if r.stderr.strip():
-            print(r.stderr.strip()[-3000:])
-    names = sorted(next(iter(out.values()))["pairs"]) if out else []
-    print("variant | step ms | pairs total ms | digest")
-    for name, d in out.items():
-        print(f"{name} | {d['ms_per_step']:.3f} | {d['pair_ms_total']} | {d['digest']}")
-    print("launch | " + " | ".join(out))
-    for n in names:
-        print(n, "|", " | ".join(str(d["pairs"].get(n)) for d in out.values()))
+    mel = fx.synthetic_mel(16, 800, seed=7).cuda()
+    models, digests = {}, {}
+    for name, env in VARIANTS:
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        m = make_generator(fx.V1, precision="bf16").cuda()
+        with torch.no_grad():
+            y = m(mel)  # the plan (and its HG_* switches) is created here
+        torch.cuda.synchronize()
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+        models[name] = m
+        digests[name] = hashlib.sha256(y.cpu().numpy().tobytes()).hexdigest()[:16]
+    step = {n: [] for n in models}
+    pairs = {n: {} for n in models}
+    with torch.no_grad():
+        for name, m in models.items():
+            for _ in range(3):
+                m(mel)
+        for _ in range(ROUNDS):
+            for name, m in models.items():
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(10):
+                    m(mel)
+                e1.record()
+                torch.cuda.synchronize()
+                step[name].append(e0.elapsed_time(e1) / 10)
+                for r in m.profile_layers(mel):
+                    if r.get("kernel") == "tcgen05 fused pair":
+                        pairs[name].setdefault(r["name"], []).append(r["ms"])
+    mean = lambda v: sum(v) / len(v)  # noqa: E731
+    print("variant | forward ms (mean of %d x 10) | min | 18 pair launches, sum of means ms | digest" % ROUNDS)
+    for n in models:
+        print(f"{n} | {mean(step[n]):.3f} | {min(step[n]):.3f} | {sum(mean(v) for v in pairs[n].values()):.3f} | {digests[n]}")
+    print("launch | " + " | ".join(models))
+    for ln in sorted(pairs["N=C"]):
+        print(ln, "|", " | ".join(f"{mean(pairs[n][ln]):.4f}" for n in models))
+    assert len(set(digests.values())) == 1, digests
 
 
 if __name__ == "__main__":

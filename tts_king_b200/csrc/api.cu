@@ -413,7 +413,7 @@ static int pack_layer(Layer& l, const float* W, const float* bias) {
   std::vector<float> bfull(l.n_total);
   for (int n = 0; n < l.n_total; ++n) bfull[n] = bias[n % l.cout];
   if ((rc = upload(bfull.data(), bfull.size() * 4, reinterpret_cast<void**>(&l.bias)))) return rc;
-  if (l.kind == L_CONV && (l.cout == 32 || l.cout == 64)) {
+  if (l.kind == L_CONV && (l.cout == 16 || l.cout == 32 || l.cout == 64)) {
     // the time-folded pair kernel's epilogue sees F = 128 / C output rows as one 128-column row
     std::vector<float> bf(128);
     for (int n = 0; n < 128; ++n) bf[n] = bias[n % l.cout];
@@ -426,6 +426,20 @@ static int pack_layer(Layer& l, const float* W, const float* bias) {
         for (int n = 0; n < l.n_total; ++n)
           wf[(static_cast<size_t>(t) * l.cin + c) * l.n_total + n] = gemm_weight(l, W, t, n, c);
     if ((rc = upload(wf.data(), wf.size() * 4, reinterpret_cast<void**>(&l.w_ffma)))) return rc;
+  }
+  if (!l.tc && l.kind == L_CONV && l.cin == 16 && l.cout == 16) {
+    // 16-channel convs have no tiling in conv_tc.cu (K chunks of 32 / 64); the time-folded pair kernel takes
+    // them as [tap][16 rows][16] tiles of 32-byte rows in the 32B-swizzle layout (chunk ^= (row >> 2) & 1)
+    const size_t tile = 16 * 32;
+    std::vector<uint8_t> hi(tile * l.k);
+    for (int t = 0; t < l.k; ++t)
+      for (int row = 0; row < 16; ++row)
+        for (int kk = 0; kk < 16; ++kk) {
+          const uint16_t h = f32_to_bf16_rn(gemm_weight(l, W, t, row, kk));
+          const size_t off = t * tile + static_cast<size_t>(row) * 32 + ((((kk >> 3) ^ ((row >> 2) & 1))) << 4) + ((kk & 7) << 1);
+          memcpy(&hi[off], &h, 2);
+        }
+    if ((rc = upload(hi.data(), hi.size(), reinterpret_cast<void**>(&l.w_hi)))) return rc;
   }
   if (l.tc) {  // swizzled bf16 tiles [n_blk][chunk][tap][n_tile rows][kc], hi and lo planes
     const int rowb = l.kc * 2;
@@ -914,9 +928,9 @@ struct FoldTiling {
 // pure geometry (no device state): also what hg_fold_info reports, so the CPU tests can replay the dataflow
 // pure geometry (no device state): also what hg_fold_info reports, so the CPU tests can replay the dataflow
 static bool fold_geometry(int c, int k, int d1, int L, FoldTiling* t) {
-  if (c != 32 && c != 64) return false;
+  if (c != 16 && c != 32 && c != 64) return false;
   const int f = 128 / c;
-  if ((k & 1) == 0 || k > kMaxTaps || k < f || k + f - 1 > kFoldMaxOps) return false;
+  if ((k & 1) == 0 || k > kMaxTaps || k + f - 1 > kFoldMaxOps) return false;
   if (L < 1 || L % f != 0 || d1 < 1 || d1 > 16) return false;
   const int rowb = c * 2, align = 1024 / rowb;
   const int ch = (k - 1) / 2;             // taps each side
@@ -965,15 +979,16 @@ static bool fold_geometry(int c, int k, int d1, int L, FoldTiling* t) {
 // is HBM-bound (k = 3) or when the epilogue also reads the MRF running sum with plain loads (its smaller output
 // tiles mean more of those epilogues).  HG_FOLD=2 forces it wherever it applies (tests, A/B).
 static bool fold_pays(const HgPlan* plan, const Layer& l2, bool mrf_accumulate) {
-  if (plan->fold_force) return true;
+  if (plan->fold_force || l2.cin == 16) return true;  // 16 channels: the alternative is the CUDA-core kernel
   if (l2.cin == 32) return l2.k >= 5 && !(mrf_accumulate && l2.k >= 9);
   return l2.k >= 9 && !mrf_accumulate;
 }
 
 static bool fold_fusable(const HgPlan* plan, const Layer& l1, const Layer& l2, int precision, int L, FoldTiling* t) {
   if (!plan->fuse_pairs || !plan->fold_pairs || precision != HG_PREC_BF16 || plan->force_ffma) return false;
-  if (l1.kind != L_CONV || l2.kind != L_CONV || !l1.tc || !l2.tc || !l2.bias_fold) return false;
+  if (l1.kind != L_CONV || l2.kind != L_CONV || !l1.w_hi || !l2.w_hi || !l2.bias_fold) return false;
   const int c = l1.cin;
+  if (!(l1.tc && l2.tc) && c != 16) return false;
   if (l1.cout != c || l2.cin != c || l2.cout != c || l1.k != l2.k || l2.dil != 1) return false;
   return fold_geometry(c, l1.k, l1.dil, L, t);
 }
@@ -1126,7 +1141,12 @@ extern "C" int hg_forward_launches(const HgPlan* plan, int B, int T, int precisi
     for (int i = 0; i < U * K; ++i, li += 2 * D)
       for (int m = 0; m < D; ++m) {
         PairTiling pt;
-        if (pair_fusable(plan, plan->layers[li + m], plan->layers[li + D + m], precision, &pt)) --n;
+        FoldTiling ft;
+        int Ls = T;  // sequence length of stage i / K
+        for (int s = 0; s <= i / K; ++s) Ls *= plan->cfg.upsample_rates[s];
+        if (pair_fusable(plan, plan->layers[li + m], plan->layers[li + D + m], precision, &pt) ||
+            fold_fusable(plan, plan->layers[li + m], plan->layers[li + D + m], precision, Ls, &ft))
+          --n;
       }
   }
   *launches = n;
@@ -1190,7 +1210,10 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
         int a_conv_in = a_in;
         const Layer& l2 = plan->layers[c.resblock_type == 1 ? li + D + m : li + m];
         PairTiling pt;
-        const bool fused = c.resblock_type == 1 && pair_fusable(plan, plan->layers[li + m], l2, precision, &pt);
+        FoldTiling ft;
+        const bool pair_ok = c.resblock_type == 1 && pair_fusable(plan, plan->layers[li + m], l2, precision, &pt);
+        const bool fold_ok = c.resblock_type == 1 && fold_fusable(plan, plan->layers[li + m], l2, precision, L, &ft);
+        const bool fused = pair_ok || fold_ok;
         if (c.resblock_type == 1 && !fused) {
           // xt = c1(leaky_relu(x)); only leaky_relu(xt) is consumed  :90-92
           const int a_t = 2;
@@ -1224,8 +1247,7 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
             }
           }
         }
-        FoldTiling ft;
-        if (fused && fold_fusable(plan, plan->layers[li + m], l2, precision, L, &ft) && fold_pays(plan, l2, ep.acc_in != nullptr)) {
+        if (fold_ok && (!pair_ok || fold_pays(plan, l2, ep.acc_in != nullptr))) {
           // ... with F = 128 / C time rows folded into the MMA's N dimension  (conv_pair_fold.cu)
           if ((rc = run_pair_fold(plan, plan->layers[li + m], l2, ft, B, L, ws.A[a_conv_in], ep, slope, st))) return rc;
         } else if (fused) {
@@ -1658,7 +1680,8 @@ extern "C" int hg_op_conv_pair(int device, const float* x, int B, int L, int C, 
   Layer& l1 = plan.layers[0];
   Layer& l2 = plan.layers[1];
   PairTiling pt;
-  if (!pair_fusable(&plan, l1, l2, HG_PREC_BF16, &pt)) return fail(HG_EINVAL, "shape not covered by the fused pair kernel");
+  const bool pair_ok = pair_fusable(&plan, l1, l2, HG_PREC_BF16, &pt);
+  if (!pair_ok && C != 16) return fail(HG_EINVAL, "shape not covered by the fused pair kernels");
   if ((rc = pack_layer(l1, w1, b1)) || (rc = pack_layer(l2, w2, b2))) { free_layer(l1); free_layer(l2); return rc; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long n = static_cast<long long>(B) * L * C;
@@ -1674,7 +1697,8 @@ extern "C" int hg_op_conv_pair(int device, const float* x, int B, int L, int C, 
   FoldTiling ft;
   if (e != cudaSuccess) rc = fail(HG_ECUDA, "f32_to_operand: %s", cudaGetErrorString(e));
   else if (fold_fusable(&plan, l1, l2, HG_PREC_BF16, L, &ft)) rc = run_pair_fold(&plan, l1, l2, ft, B, L, in, ep, in_slope, st);
-  else rc = run_pair(&plan, l1, l2, pt, B, L, in, ep, in_slope, st);
+  else if (pair_ok) rc = run_pair(&plan, l1, l2, pt, B, L, in, ep, in_slope, st);
+  else rc = fail(HG_EINVAL, "shape not covered by the fused pair kernels (16 channels need L %% 8 == 0)");
   cudaError_t es = cudaStreamSynchronize(st);
   cudaFree(a);
   free_layer(l1); free_layer(l2);

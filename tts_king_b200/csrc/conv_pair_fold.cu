@@ -1,5 +1,5 @@
 // conv_pair_fold.cu — one ResBlock1 pair as a single tcgen05 kernel with TIME FOLDED INTO N
-// (bf16 mode, C = 32 or 64):
+// (bf16 mode, C = 16, 32 or 64):
 //
 //     xt = leaky_relu(c1(a) + b1)          dilated Conv1d, hifi/models.py:90-92
 //     y  = c2(xt) + b2 + x                 Conv1d d=1 + residual, hifi/models.py:93-94
@@ -152,8 +152,8 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
   const int STAGES = RING ? p.stages : 2 * K;
   constexpr uint32_t ACC_COLS = 128;
   constexpr uint32_t TMEM_COLS = 4 * ACC_COLS;
-  static_assert(C == 64 || C == 32, "C = 16 needs the half-swapped E2 item");
-  static_assert(K >= F && (K & 1), "every phase must be covered by one group; odd taps");
+  static_assert(C == 64 || C == 32 || C == 16, "N = 128 = F x C");
+  static_assert(K & 1, "odd taps");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -344,7 +344,9 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
     const int blk1 = mrow / p.d1, r1 = mrow - blk1 * p.d1;
     // E2: this warp's 32-column item; accumulator column block q holds phase F-1-q
     const int c02 = sub * 32;                                   // accumulator columns
-    const int c02m = (F - 1 - c02 / C) * C + (c02 % C);         // columns of the folded output row
+    // columns of the folded output row this item lands on.  At C = 16 the item spans two phases, stored in
+    // the accumulator in descending phase order: its two 16-column halves are swapped relative to memory.
+    const int c02m = (C >= 32) ? (F - 1 - c02 / C) * C + (c02 % C) : (F - (c02 + 32) / C) * C;
 
     // E1: D1 -> (+b1, leaky_relu, bf16) -> xt phase slabs in UMMA layout; two 16-column items per warp
     auto e1 = [&](int i) {
@@ -446,8 +448,9 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
         for (int k4 = 0; k4 < 8; ++k4) {
           float4* sp = reinterpret_cast<float4*>(stg + lane * 32 + ((k4 ^ (lane & 7)) << 2));
           float4 t = *sp;
-          t.x += __uint_as_float(r[4 * k4]); t.y += __uint_as_float(r[4 * k4 + 1]);
-          t.z += __uint_as_float(r[4 * k4 + 2]); t.w += __uint_as_float(r[4 * k4 + 3]);
+          const int ka = (C >= 32) ? k4 : (k4 ^ 4);  // accumulator float4 that belongs to memory float4 k4
+          t.x += __uint_as_float(r[4 * ka]); t.y += __uint_as_float(r[4 * ka + 1]);
+          t.z += __uint_as_float(r[4 * ka + 2]); t.w += __uint_as_float(r[4 * ka + 3]);
           *sp = t;
         }
       }
@@ -489,9 +492,10 @@ size_t conv_fold_smem_bytes(int c, int slab_phase_bytes, int xt_phase_bytes, int
          static_cast<size_t>(stages) * c * c * 2 + (34 + 2 * stages) * 8 + 16;
 }
 
-// (C, k, streamed?) combinations the kernel is instantiated for: C = 32 keeps its weights resident for every
-// k; C = 64 does for k = 3 and streams from k = 5 on
+// (C, k, streamed?) combinations the kernel is instantiated for: C = 16 / 32 keep their weights resident for
+// every k; C = 64 does for k = 3 and streams from k = 5 on.  (C = 32, k = 3 is left to conv_pair_tc.cu.)
 bool conv_fold_has_kernel(int c, int k, bool ring) {
+  if (c == 16) return !ring && (k == 3 || k == 5 || k == 7 || k == 9 || k == 11);
   if (c == 32) return !ring && (k == 5 || k == 7 || k == 9 || k == 11);
   if (c == 64) return ring ? (k == 5 || k == 7 || k == 9 || k == 11) : k == 3;
   return false;
@@ -522,6 +526,7 @@ cudaError_t launch_conv_pair_fold(int c, int k, bool ring, const CUtensorMap& m,
   if (!conv_fold_has_kernel(c, k, ring)) return cudaErrorInvalidValue;
 #define HG_FOLD_CASE(CV, KV, RV) \
   if (c == CV && k == KV && ring == RV) return launch_fold<CV, KV, RV>(m, mr, p, smem, grid, st);
+  HG_FOLD_CASE(16, 3, false) HG_FOLD_CASE(16, 5, false) HG_FOLD_CASE(16, 7, false) HG_FOLD_CASE(16, 9, false) HG_FOLD_CASE(16, 11, false)
   HG_FOLD_CASE(32, 5, false) HG_FOLD_CASE(32, 7, false) HG_FOLD_CASE(32, 9, false) HG_FOLD_CASE(32, 11, false)
   HG_FOLD_CASE(64, 3, false)
   HG_FOLD_CASE(64, 5, true) HG_FOLD_CASE(64, 7, true) HG_FOLD_CASE(64, 9, true) HG_FOLD_CASE(64, 11, true)
