@@ -120,7 +120,7 @@ def test_conv1d_fp32_mode_is_fp32_accurate():
 
 @pytest.mark.parametrize("prec", ["fp32_ffma", "fp32", "bf16"])
 @pytest.mark.parametrize("cin,cout,k,s", [(512, 256, 16, 8), (256, 128, 16, 8), (128, 64, 4, 2), (64, 32, 4, 2),
-                                          (256, 128, 8, 4)])
+                                          (256, 128, 8, 4), (16, 16, 4, 2), (16, 16, 16, 8), (16, 8, 4, 2)])
 def test_conv_transpose1d_parity(cin, cout, k, s, prec):
     L = _native.lib()
     g = torch.Generator().manual_seed(cin + k)
@@ -136,7 +136,9 @@ def test_conv_transpose1d_parity(cin, cout, k, s, prec):
     torch.cuda.synchronize()
     y = y.cpu().transpose(1, 2)
     a = operand_model(F.leaky_relu(x, 0.1), prec)
-    ww = operand_model(w, prec)
+    # 16 input channels have no tensor-core tiling: CUDA-core kernels, whose weights stay fp32 (convt_narrow16 in
+    # bf16 mode when C_out = 16 too — the upsampler in front of a stage padded to 16 channels — conv_ffma otherwise)
+    ww = operand_model(w, prec) if cin != 16 else w.double()
     ref = F.conv_transpose1d(a, ww, b.double(), stride=s, padding=(k - s) // 2)
     assert not torch.isnan(y).any()
     assert (y.double() - ref).abs().max().item() <= TOL[prec] * ref.abs().max().item()

@@ -28,6 +28,8 @@ cudaError_t launch_f32_to_operand(const float* x, long long n, float slope, int 
                                   cudaStream_t st);
 int run_tcgen05_selftest(char* buf, size_t len);
 cudaError_t launch_conv_narrow(int c, NarrowConvParams p, cudaStream_t st, const RaggedItems* items = nullptr);
+cudaError_t launch_convt_narrow16(const void* a, const float* w_tap_cin_n, int B, int L_in, int stride, int pad, EpiParams epi,
+                                  cudaStream_t st, const RaggedItems* items = nullptr);
 size_t conv_pair_smem_bytes(int c, int slab_rows, int t_rows, int t_bufs, int stages);
 size_t conv_tc2_smem_bytes(int n_t, int slab_rows, int nbuf, int stages, int epi_slot_bytes);
 cudaError_t launch_conv_tc2(int n_t, int ms, const CUtensorMap* maps, const TcConvParams& p, size_t smem, int grid,
@@ -357,8 +359,51 @@ extern "C" int hg_plan_create(const HgConfig* cfg, int device, HgPlan** out) {
   post.name = "conv_post"; post.kind = L_POST; post.cin = ch; post.cout = 1; post.k = 7; post.pad = 3;
   p->layers.push_back(post);
   for (size_t i = 0; i < p->layers.size(); ++i) p->by_name[p->layers[i].name] = static_cast<int>(i);
+  // Stages narrower than 16 channels (V2-style configs end at 8) have no tensor-core tiling: K = 16 is the
+  // smallest bf16 MMA.  For the bf16 schedule they are carried zero-padded to 16 channels — weights, bias and
+  // activations; a padded channel is 0 everywhere, so nothing changes for the real ones — and run on the
+  // 16-channel kernels.  The fp32 schedules keep the exact shapes (CUDA-core kernels).
+  if (env_int("HG_PAD_NARROW", 1)) {
+    std::vector<Layer> padded = p->layers;
+    bool any = false;
+    int li = 1 + cfg->num_upsamples;
+    const int per_stage = cfg->num_kernels * (cfg->resblock_type == 1 ? 2 * D : D);
+    for (int i = 0; i < cfg->num_upsamples; ++i, li += per_stage) {
+      const int c = uic >> (i + 1);
+      if (c >= 16) continue;
+      any = true;
+      auto repad = [&](Layer& l, int cin, int cout) {
+        Layer n = l.kind == L_CONVT ? make_convT(l.name, cin, cout, l.k, l.stride) : make_conv(l.name, cin, cout, l.k, l.dil);
+        n.cin_w = l.cin_w ? l.cin_w : l.cin;
+        n.cout_w = l.cout_w ? l.cout_w : l.cout;
+        l = n;
+      };
+      Layer& up = padded[1 + i];
+      repad(up, up.cin, 16);
+      for (int q = 0; q < per_stage; ++q) repad(padded[li + q], 16, 16);
+      if (i + 1 < cfg->num_upsamples) {
+        Layer& nx = padded[2 + i];
+        repad(nx, 16, nx.cout);
+      } else {
+        Layer& po = padded.back();
+        po.cin_w = po.cin;
+        po.cin = 16;
+      }
+    }
+    if (any) p->layers_pad = padded;
+  }
   *out = p;
   return HG_OK;
+}
+
+// the layer table a forward in `precision` runs on (see hg_plan_create)
+static const std::vector<Layer>& active_layers(const HgPlan* plan, int precision) {
+  return (precision == HG_PREC_BF16 && !plan->layers_pad.empty() && !plan->force_ffma) ? plan->layers_pad : plan->layers;
+}
+static int layer_index(const HgPlan* plan, const Layer* l) {
+  if (!plan->layers_pad.empty() && l >= plan->layers_pad.data() && l < plan->layers_pad.data() + plan->layers_pad.size())
+    return static_cast<int>(l - plan->layers_pad.data());
+  return static_cast<int>(l - plan->layers.data());
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -379,11 +424,12 @@ static inline float bf16_to_f32(uint16_t h) {
 
 // GEMM-view weight Wg(tap, n, c) from the reference layouts.
 static inline float gemm_weight(const Layer& l, const float* W, int t, int n, int c) {
-  if (c >= l.cin) return 0.f;
-  if (l.kind == L_CONV) return W[(static_cast<size_t>(n) * l.cin + c) * l.k + t];
+  const int cin_w = l.cin_w ? l.cin_w : l.cin, cout_w = l.cout_w ? l.cout_w : l.cout;  // dims of W itself
+  if (c >= cin_w) return 0.f;
+  if (l.kind == L_CONV) return n < cout_w ? W[(static_cast<size_t>(n) * cin_w + c) * l.k + t] : 0.f;
   const int r = n / l.cout, o = n % l.cout;
   const int j = r + l.stride * t;
-  return j < l.k ? W[(static_cast<size_t>(c) * l.cout + o) * l.k + j] : 0.f;
+  return (j < l.k && o < cout_w) ? W[(static_cast<size_t>(c) * cout_w + o) * l.k + j] : 0.f;
 }
 
 static int upload(const void* host, size_t bytes, void** dev) {
@@ -400,10 +446,11 @@ static void free_layer(Layer& l) {
 
 static int pack_layer(Layer& l, const float* W, const float* bias) {
   int rc;
+  const int cin_w = l.cin_w ? l.cin_w : l.cin, cout_w = l.cout_w ? l.cout_w : l.cout;
   if (l.kind == L_POST) {
-    std::vector<float> wp(static_cast<size_t>(l.k) * l.cin);
+    std::vector<float> wp(static_cast<size_t>(l.k) * l.cin, 0.f);
     for (int j = 0; j < l.k; ++j)
-      for (int c = 0; c < l.cin; ++c) wp[static_cast<size_t>(j) * l.cin + c] = W[static_cast<size_t>(c) * l.k + j];
+      for (int c = 0; c < cin_w; ++c) wp[static_cast<size_t>(j) * l.cin + c] = W[static_cast<size_t>(c) * l.k + j];
     if ((rc = upload(wp.data(), wp.size() * 4, reinterpret_cast<void**>(&l.w_post)))) return rc;
     l.w_post_host = wp;
     l.bias_post = bias[0];
@@ -411,12 +458,12 @@ static int pack_layer(Layer& l, const float* W, const float* bias) {
     return HG_OK;
   }
   std::vector<float> bfull(l.n_total);
-  for (int n = 0; n < l.n_total; ++n) bfull[n] = bias[n % l.cout];
+  for (int n = 0; n < l.n_total; ++n) bfull[n] = (n % l.cout) < cout_w ? bias[n % l.cout] : 0.f;
   if ((rc = upload(bfull.data(), bfull.size() * 4, reinterpret_cast<void**>(&l.bias)))) return rc;
   if (l.kind == L_CONV && (l.cout == 16 || l.cout == 32 || l.cout == 64)) {
     // the time-folded pair kernel's epilogue sees F = 128 / C output rows as one 128-column row
     std::vector<float> bf(128);
-    for (int n = 0; n < 128; ++n) bf[n] = bias[n % l.cout];
+    for (int n = 0; n < 128; ++n) bf[n] = (n % l.cout) < cout_w ? bias[n % l.cout] : 0.f;
     if ((rc = upload(bf.data(), bf.size() * 4, reinterpret_cast<void**>(&l.bias_fold)))) return rc;
   }
   {  // CUDA-core layout [tap][cin][n_total]
@@ -479,13 +526,18 @@ extern "C" int hg_plan_upload_weight(HgPlan* plan, const char* name, const float
   int64_t want[3];
   if (l.kind == L_CONVT) { want[0] = l.cin; want[1] = l.cout; want[2] = l.k; }
   else { want[0] = l.cout; want[1] = l.cin; want[2] = l.k; }
+  if (l.kind == L_POST) { want[0] = 1; want[1] = l.cin; want[2] = l.k; }
   if (ndim != 3 || shape[0] != want[0] || shape[1] != want[1] || shape[2] != want[2])
     return fail(HG_EINVAL, "size mismatch for %s.weight: expected [%lld,%lld,%lld]", name,
                 static_cast<long long>(want[0]), static_cast<long long>(want[1]), static_cast<long long>(want[2]));
   if (bias_len != l.cout) return fail(HG_EINVAL, "size mismatch for %s.bias: expected [%d]", name, l.cout);
   DEVICE_SCOPE(plan->device);
   if (l.loaded) free_layer(l);
-  return pack_layer(l, weight, bias);
+  int rc = pack_layer(l, weight, bias);
+  if (rc || plan->layers_pad.empty()) return rc;
+  Layer& lp = plan->layers_pad[it->second];  // the same tensors, zero-padded, for the bf16 schedule
+  if (lp.loaded) free_layer(lp);
+  return pack_layer(lp, weight, bias);
 }
 
 extern "C" int hg_plan_finalize(HgPlan* plan) {
@@ -500,6 +552,7 @@ extern "C" int hg_plan_destroy(HgPlan* plan) {
   if (!plan) return HG_OK;
   DeviceScope scope(plan->device);
   for (auto& l : plan->layers) free_layer(l);
+  for (auto& l : plan->layers_pad) free_layer(l);
   delete plan;
   return HG_OK;
 }
@@ -720,7 +773,7 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
         const size_t smem = conv_tc2_smem_bytes(l.n_tile, slab_rows, nbuf, stages, slot);
         cudaError_t e = launch_conv_tc2(l.n_tile, ms, maps, p, smem, 2 * pairs, st);
         if (e != cudaSuccess) return fail(HG_ECUDA, "conv_tc2 launch (%s): %s", l.name.c_str(), cudaGetErrorString(e));
-        if (g_prof) prof_mark(static_cast<int>(&l - plan->layers.data()), make_rec(HG_PATH_TC_CTA_PAIR, l.n_tile, 64, ms, stages, nbuf, false, smem));
+        if (g_prof) prof_mark(layer_index(plan, &l), make_rec(HG_PATH_TC_CTA_PAIR, l.n_tile, 64, ms, stages, nbuf, false, smem));
         return HG_OK;
       }
     }
@@ -781,7 +834,7 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
                 l.name.c_str(), grid, n / grid, tot / grid, a / grid, 100 * a / tot, sl / grid, 100 * sl / tot, w / grid, 100 * w / tot);
       }
       if (e != cudaSuccess) return fail(HG_ECUDA, "conv_tc launch (%s): %s", l.name.c_str(), cudaGetErrorString(e));
-      if (g_prof) prof_mark(static_cast<int>(&l - plan->layers.data()), make_rec(HG_PATH_TC, l.n_tile, l.kc, t.ms, t.stages, t.nbuf, t.resident, t.smem));
+      if (g_prof) prof_mark(layer_index(plan, &l), make_rec(HG_PATH_TC, l.n_tile, l.kc, t.ms, t.stages, t.nbuf, t.resident, t.smem));
       return HG_OK;
     }
   }
@@ -794,7 +847,15 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
     np.w = l.w_ffma; np.epi = epi;
     cudaError_t e = launch_conv_narrow(l.cin, np, st, rag);
     if (e != cudaSuccess) return fail(HG_ECUDA, "conv_narrow launch (%s): %s", l.name.c_str(), cudaGetErrorString(e));
-    if (g_prof) prof_mark(static_cast<int>(&l - plan->layers.data()), make_rec(HG_PATH_NARROW));
+    if (g_prof) prof_mark(layer_index(plan, &l), make_rec(HG_PATH_NARROW));
+    return HG_OK;
+  }
+  // 16 -> 16 channel upsampler with two taps per phase (the step into a stage that runs padded to 16 channels)
+  if (l.kind == L_CONVT && l.cin == 16 && l.cout == 16 && l.ntaps == 2 && precision == HG_PREC_BF16 && !plan->force_ffma &&
+      !epi.res && !epi.acc_in && epi.post_div <= 0.f) {
+    cudaError_t e = launch_convt_narrow16(in.a0, l.w_ffma, B, L_in, l.stride, l.pad, epi, st, rag);
+    if (e != cudaSuccess) return fail(HG_ECUDA, "convt_narrow16 launch (%s): %s", l.name.c_str(), cudaGetErrorString(e));
+    if (g_prof) prof_mark(layer_index(plan, &l), make_rec(HG_PATH_NARROW));
     return HG_OK;
   }
   FfmaConvParams f;
@@ -806,7 +867,7 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
   f.w = l.w_ffma; f.epi = epi;
   cudaError_t e = launch_conv_ffma(f, st, rag);
   if (e != cudaSuccess) return fail(HG_ECUDA, "conv_ffma launch (%s): %s", l.name.c_str(), cudaGetErrorString(e));
-  if (g_prof) prof_mark(static_cast<int>(&l - plan->layers.data()), make_rec(HG_PATH_CUDA_CORE));
+  if (g_prof) prof_mark(layer_index(plan, &l), make_rec(HG_PATH_CUDA_CORE));
   return HG_OK;
 }
 
@@ -912,7 +973,7 @@ static int run_pair(HgPlan* plan, const Layer& l1, const Layer& l2, const PairTi
             s[11], s[12], s[13], s[14]);
   }
   if (e != cudaSuccess) return fail(HG_ECUDA, "conv_pair_tc launch (%s): %s", l2.name.c_str(), cudaGetErrorString(e));
-  if (g_prof) prof_mark(static_cast<int>(&l2 - plan->layers.data()), make_rec(HG_PATH_FUSED_PAIR, c, c, t.ms, t.stages, 2, t.resident, t.smem));
+  if (g_prof) prof_mark(layer_index(plan, &l2), make_rec(HG_PATH_FUSED_PAIR, c, c, t.ms, t.stages, 2, t.resident, t.smem));
   return HG_OK;
 }
 
@@ -1056,7 +1117,7 @@ static int run_pair_fold(HgPlan* plan, const Layer& l1, const Layer& l2, const F
   const int grid = std::min(p.total_work, plan->sm_count);
   cudaError_t e = launch_conv_pair_fold(c, l1.k, !t.resident, m, mr, p, t.smem, grid, st);
   if (e != cudaSuccess) return fail(HG_ECUDA, "conv_pair_fold launch (%s): %s", l2.name.c_str(), cudaGetErrorString(e));
-  if (g_prof) prof_mark(static_cast<int>(&l2 - plan->layers.data()), make_rec(HG_PATH_FUSED_PAIR, 128, c, 1, t.stages, 2, t.resident, t.smem));
+  if (g_prof) prof_mark(layer_index(plan, &l2), make_rec(HG_PATH_FUSED_PAIR, 128, c, 1, t.stages, 2, t.resident, t.smem));
   return HG_OK;
 }
 
@@ -1073,7 +1134,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // channel pitch of the mel operand: padded only when conv_pre runs on the tensor-core path
 static int mel_pitch(const HgPlan* plan, int precision) {
-  const Layer& pre = plan->layers[0];
+  const Layer& pre = active_layers(plan, precision)[0];
   return use_tc(plan, pre, precision) ? pre.cin_pad : pre.cin;
 }
 
@@ -1082,7 +1143,7 @@ static int layout_workspace(const HgPlan* plan, int B, int T, int precision, voi
   long long L = T;
   long long max_e = static_cast<long long>(B) * T * c.upsample_initial_channel;
   for (int i = 0; i < c.num_upsamples; ++i) {
-    const Layer& up = plan->layers[1 + i];
+    const Layer& up = active_layers(plan, precision)[1 + i];
     L = (L - 1) * up.stride - 2 * up.pad + up.k;
     if (L < 1) return fail(HG_EINVAL, "input too short for upsampler %d", i);
     max_e = std::max(max_e, static_cast<long long>(B) * L * up.cout);
@@ -1134,7 +1195,8 @@ extern "C" int hg_forward_launches(const HgPlan* plan, int B, int T, int precisi
   int rc = check_fwd_args(plan, B, T, precision);
   if (rc) return rc;
   if (!launches) return fail(HG_EINVAL, "null launches");
-  int n = static_cast<int>(plan->layers.size()) + 1;  // every layer + the mel repack
+  const std::vector<Layer>& LY = active_layers(plan, precision);
+  int n = static_cast<int>(LY.size()) + 1;  // every layer + the mel repack
   if (plan->cfg.resblock_type == 1) {
     const int D = 3, U = plan->cfg.num_upsamples, K = plan->cfg.num_kernels;
     int li = 1 + U;
@@ -1144,8 +1206,8 @@ extern "C" int hg_forward_launches(const HgPlan* plan, int B, int T, int precisi
         FoldTiling ft;
         int Ls = T;  // sequence length of stage i / K
         for (int s = 0; s <= i / K; ++s) Ls *= plan->cfg.upsample_rates[s];
-        if (pair_fusable(plan, plan->layers[li + m], plan->layers[li + D + m], precision, &pt) ||
-            fold_fusable(plan, plan->layers[li + m], plan->layers[li + D + m], precision, Ls, &ft))
+        if (pair_fusable(plan, LY[li + m], LY[li + D + m], precision, &pt) ||
+            fold_fusable(plan, LY[li + m], LY[li + D + m], precision, Ls, &ft))
           --n;
       }
   }
@@ -1170,6 +1232,7 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
   DEVICE_SCOPE(plan->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const HgConfig& c = plan->cfg;
+  const std::vector<Layer>& LY = active_layers(plan, precision);
   const int fmt = a_fmt_of(precision);
   const int U = c.num_upsamples, K = c.num_kernels, D = rb_dilations(c);
   const float slope = 0.1f;  // LRELU_SLOPE, hifi/models.py:9
@@ -1186,13 +1249,13 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
   {
     EpiParams ep; memset(&ep, 0, sizeof(ep));
     ep.out_a0 = ws.A[a_cur].a0; ep.out_a1 = ws.A[a_cur].a1; ep.slope = slope;
-    if ((rc = run_layer(plan, plan->layers[0], precision, B, T, ws.mel, ep, st))) return rc;
+    if ((rc = run_layer(plan, LY[0], precision, B, T, ws.mel, ep, st))) return rc;
   }
   int L = T;
   int li = 1 + U;  // first resblock layer
   float* x_final = nullptr;
   for (int i = 0; i < U; ++i) {
-    const Layer& up = plan->layers[1 + i];
+    const Layer& up = LY[1 + i];
     const bool last_stage = i == U - 1;
     // x = ups[i](leaky_relu(x))  :188-189  -> residual stream F0 and operand A0
     {
@@ -1208,18 +1271,18 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
       for (int m = 0; m < D; ++m) {
         const bool last_pair = m == D - 1;
         int a_conv_in = a_in;
-        const Layer& l2 = plan->layers[c.resblock_type == 1 ? li + D + m : li + m];
+        const Layer& l2 = LY[c.resblock_type == 1 ? li + D + m : li + m];
         PairTiling pt;
         FoldTiling ft;
-        const bool pair_ok = c.resblock_type == 1 && pair_fusable(plan, plan->layers[li + m], l2, precision, &pt);
-        const bool fold_ok = c.resblock_type == 1 && fold_fusable(plan, plan->layers[li + m], l2, precision, L, &ft);
+        const bool pair_ok = c.resblock_type == 1 && pair_fusable(plan, LY[li + m], l2, precision, &pt);
+        const bool fold_ok = c.resblock_type == 1 && fold_fusable(plan, LY[li + m], l2, precision, L, &ft);
         const bool fused = pair_ok || fold_ok;
         if (c.resblock_type == 1 && !fused) {
           // xt = c1(leaky_relu(x)); only leaky_relu(xt) is consumed  :90-92
           const int a_t = 2;
           EpiParams ep; memset(&ep, 0, sizeof(ep));
           ep.out_a0 = ws.A[a_t].a0; ep.out_a1 = ws.A[a_t].a1; ep.slope = slope;
-          if ((rc = run_layer(plan, plan->layers[li + m], precision, B, L, ws.A[a_in], ep, st))) return rc;
+          if ((rc = run_layer(plan, LY[li + m], precision, B, L, ws.A[a_in], ep, st))) return rc;
           a_conv_in = a_t;
         }
         // x = c2(xt) + x  :93-94 (ResBlock2: x = c(leaky_relu(x)) + x  :136-138)
@@ -1249,10 +1312,10 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
         }
         if (fold_ok && (!pair_ok || fold_pays(plan, l2, ep.acc_in != nullptr))) {
           // ... with F = 128 / C time rows folded into the MMA's N dimension  (conv_pair_fold.cu)
-          if ((rc = run_pair_fold(plan, plan->layers[li + m], l2, ft, B, L, ws.A[a_conv_in], ep, slope, st))) return rc;
+          if ((rc = run_pair_fold(plan, LY[li + m], l2, ft, B, L, ws.A[a_conv_in], ep, slope, st))) return rc;
         } else if (fused) {
           // c1 and c2 in one kernel; xt never leaves shared memory  (conv_pair_tc.cu)
-          if ((rc = run_pair(plan, plan->layers[li + m], l2, pt, B, L, ws.A[a_conv_in], ep, slope, st))) return rc;
+          if ((rc = run_pair(plan, LY[li + m], l2, pt, B, L, ws.A[a_conv_in], ep, slope, st))) return rc;
         } else if ((rc = run_layer(plan, l2, precision, B, L, ws.A[a_conv_in], ep, st))) {
           return rc;
         }
@@ -1261,7 +1324,7 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
     }
   }
   // x = tanh(conv_post(leaky_relu(x)))  :197-199  (+ optional int16 tail, hifiapi.py:50-51)
-  const Layer& post = plan->layers.back();
+  const Layer& post = LY.back();
   RaggedItems rag_store;
   e = launch_conv_post(x_final, B, L, post.cin, post.w_post, post.bias_post,
                        out_dtype == HG_OUT_F32 ? static_cast<float*>(out) : nullptr,
@@ -1270,7 +1333,7 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
                        ragged_items(&rag_store, B, L, 0, /*with_halo=*/false),  // the last layer feeds nobody
                        g_win ? g_win->item_stride : 0, g_win ? g_win->skip : 0, g_win ? g_win->keep : 0);
   if (e != cudaSuccess) return fail(HG_ECUDA, "conv_post: %s", cudaGetErrorString(e));
-  prof_mark(static_cast<int>(plan->layers.size()) - 1, make_rec(HG_PATH_POST));
+  prof_mark(static_cast<int>(LY.size()) - 1, make_rec(HG_PATH_POST));
   return HG_OK;
 }
 

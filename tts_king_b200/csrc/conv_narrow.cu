@@ -124,6 +124,95 @@ static cudaError_t launch_narrow_c(const NarrowConvParams& p, int total_tiles, c
 }
 
 // C must be 8 or 16; k odd.
+// ------------------------------------------------------------------------------------------------
+// ConvTranspose1d 16 -> 16 channels, stride s, kernel 2s (two taps per output phase), bf16 operands: the
+// upsampler in front of a stage that runs zero-padded to 16 channels (V2-style: 16 -> 8, ups.3).  A
+// [L_in*s rows] x [16] output from a [L_in] x [16] input is 32 MACs per output element — nothing for a
+// tensor core to do; it is a streaming kernel: one thread per output row reads its two input rows (32 B
+// each), contracts them with the phase's [2][16][16] weight slice from shared memory and writes the fp32 row
+// (64 B) and the bf16 operand row (32 B).  Polyphase form of SURVEY.md A.3 (reference hifi/models.py:161-171).
+constexpr int kConvtRows = 256;
+
+__global__ void __launch_bounds__(kConvtRows) convt_narrow16_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w,
+                                                                    int L_in, int stride, int pad, int tiles_per_item,
+                                                                    const RaggedPrefix rag, const EpiParams e) {
+  extern __shared__ __align__(16) float cws[];  // [2 taps][16 c_in][stride*16]
+  const int n_total = stride * 16;
+  for (int i = threadIdx.x; i < 2 * 16 * n_total; i += kConvtRows) cws[i] = w[i];
+  __syncthreads();
+  int b, tile;
+  decode_tile(rag, tiles_per_item, static_cast<int>(blockIdx.x), b, tile);
+  const int L_out = L_in * stride;
+  const int n = tile * kConvtRows + threadIdx.x;  // output row
+  if (n >= L_out) return;
+  const int q = (n + pad) / stride, r = (n + pad) - q * stride;  // y[n] = sum_m W[., ., r + s*m] x[q - m]
+  float acc[16];
+#pragma unroll
+  for (int o = 0; o < 16; ++o) acc[o] = e.bias[o];
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    const int row = q - m;
+    if (row < 0 || row >= L_in) continue;
+    const uint4* ap = reinterpret_cast<const uint4*>(a + (static_cast<long long>(b) * L_in + row) * 16);
+    const uint4 h0 = ap[0], h1 = ap[1];
+    const __nv_bfloat162* p0 = reinterpret_cast<const __nv_bfloat162*>(&h0);
+    const __nv_bfloat162* p1 = reinterpret_cast<const __nv_bfloat162*>(&h1);
+    float x[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      x[2 * i] = __low2float(p0[i]); x[2 * i + 1] = __high2float(p0[i]);
+      x[8 + 2 * i] = __low2float(p1[i]); x[8 + 2 * i + 1] = __high2float(p1[i]);
+    }
+    const float* wm = cws + (m * 16) * n_total + r * 16;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float4* wr = reinterpret_cast<const float4*>(wm + c * n_total);
+#pragma unroll
+      for (int o4 = 0; o4 < 4; ++o4) {
+        const float4 ww = wr[o4];
+        acc[4 * o4] = fmaf(x[c], ww.x, acc[4 * o4]); acc[4 * o4 + 1] = fmaf(x[c], ww.y, acc[4 * o4 + 1]);
+        acc[4 * o4 + 2] = fmaf(x[c], ww.z, acc[4 * o4 + 2]); acc[4 * o4 + 3] = fmaf(x[c], ww.w, acc[4 * o4 + 3]);
+      }
+    }
+  }
+  const long long idx = (static_cast<long long>(b) * L_out + n) * 16;
+  if (e.out_x) {
+    float4* xp = reinterpret_cast<float4*>(e.out_x + idx);
+#pragma unroll
+    for (int o4 = 0; o4 < 4; ++o4) xp[o4] = make_float4(acc[4 * o4], acc[4 * o4 + 1], acc[4 * o4 + 2], acc[4 * o4 + 3]);
+  }
+  if (e.out_a0) {
+    uint2* hp = reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(e.out_a0) + idx);
+#pragma unroll
+    for (int o4 = 0; o4 < 4; ++o4)
+      hp[o4] = pack_bf16x4(lrelu_fast(acc[4 * o4], e.slope), lrelu_fast(acc[4 * o4 + 1], e.slope),
+                           lrelu_fast(acc[4 * o4 + 2], e.slope), lrelu_fast(acc[4 * o4 + 3], e.slope));
+  }
+}
+
+// w: the layer's CUDA-core weight image [2 taps][16][stride*16] (plan.h w_ffma); epi.bias: [stride*16], first 16 used
+cudaError_t launch_convt_narrow16(const void* a, const float* w, int B, int L_in, int stride, int pad, EpiParams epi,
+                                  cudaStream_t st, const RaggedItems* items) {
+  const int L_out = L_in * stride;
+  RaggedItems out_items;
+  const RaggedItems* it = nullptr;
+  if (items && items->n) {  // valid GEMM rows of the input -> valid output rows
+    out_items.n = items->n;
+    for (int b = 0; b < items->n; ++b) {
+      const long long v = static_cast<long long>(items->valid_rows[b]) * stride;
+      out_items.valid_rows[b] = static_cast<int>(v < L_out ? v : L_out);
+    }
+    it = &out_items;
+  }
+  RaggedPrefix rag;
+  const int total = ragged_fill(&rag, it, B, L_out, kConvtRows);
+  const size_t smem = static_cast<size_t>(2) * 16 * stride * 16 * sizeof(float);
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  convt_narrow16_kernel<<<static_cast<unsigned>(total), kConvtRows, smem, st>>>(static_cast<const __nv_bfloat16*>(a), w, L_in, stride,
+                                                                                pad, (L_out + kConvtRows - 1) / kConvtRows, rag, epi);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_conv_narrow(int c, NarrowConvParams p, cudaStream_t st, const RaggedItems* items) {
   p.tiles_per_item = (p.L + kNarrowRows - 1) / kNarrowRows;
   const int total = ragged_fill(&p.rag, items, p.B, p.L, kNarrowRows);

@@ -23,6 +23,9 @@ struct Layer {
   std::string name;  // state_dict prefix
   int kind = L_CONV;
   int cin = 0, cout = 0, k = 0, dil = 1, stride = 1, pad = 0;
+  // channel counts of the state_dict tensors when this layer runs zero-padded to cin / cout channels in
+  // memory (the bf16 schedule of stages narrower than 16 channels); 0 = not padded
+  int cin_w = 0, cout_w = 0;
   // GEMM view
   int ntaps = 0;
   int tap_off[kMaxTaps] = {0};  // input row = GEMM row + tap_off
@@ -100,6 +103,9 @@ struct HgPlan {
   int sm_count = 148;
   bool finalized = false;
   std::vector<hg::Layer> layers;
+  // bf16 schedule when a stage has fewer than 16 channels: the same layers with that stage's tensors padded
+  // to 16 channels (zero weights / bias), so that it runs on the tensor-core kernels; empty otherwise
+  std::vector<hg::Layer> layers_pad;
   std::map<std::string, int> by_name;
   int desc_mode = 0;  // measured on B200 (selftest.cu): UMMA swizzle phase comes from absolute smem address bits
   int force_ms = 0, force_stages = 0;
