@@ -360,7 +360,7 @@ def test_multi_gpu_sharding_matches_single_gpu():
         assert res[prec]["direct_p2p_store_bitwise_equal"]  # gather fused into conv_post's stores (NVLink P2P)
 
 
-@pytest.mark.parametrize("env", [{"HG_TC2": "0"}, {"HG_FUSE_PAIRS": "0"}, {"HG_EPI_TMA": "0"}, {"HG_FOLD": "0"}, {"HG_FOLD": "2"},
+@pytest.mark.parametrize("env", [{"HG_TC2": "0"}, {"HG_FUSE_PAIRS": "0"}, {"HG_EPI_TMA": "0"}, {"HG_FOLD": "0"}, {"HG_FOLD": "2"}, {"HG_PAD_NARROW": "0"},
                                  {"HG_TC2": "0", "HG_FUSE_PAIRS": "0", "HG_EPI_TMA": "0"}, {"HG_FORCE_FFMA": "1"}])
 def test_alternative_kernel_paths_keep_parity(env):
     """Every layer has more than one kernel path (CTA-pair / single-CTA tcgen05, fused / unfused
@@ -378,12 +378,14 @@ def test_alternative_kernel_paths_keep_parity(env):
         "from oracle import fixtures as fx\n"
         "from oracle.common import max_abs, snr_db\n"
         "from _util import golden, make_generator\n"
-        "g = golden('v1_seed1234'); out = {}\n"
-        "for prec in ('fp32', 'bf16'):\n"
-        "    m = make_generator(fx.V1, precision=prec).cuda()\n"
-        "    with torch.no_grad():\n"
-        "        y = m(torch.from_numpy(g['mel_b']).cuda()).cpu().numpy()\n"
-        "    out[prec] = [max_abs(y, g['y_b']), snr_db(g['y_b'], y)]\n"
+        "out = {'fp32': [0.0, 1e9], 'bf16': [0.0, 1e9]}\n"
+        "for name, cfg in (('v1', fx.V1), ('v2_narrow', fx.V2_NARROW)):\n"
+        "    g = golden(name + '_seed1234')\n"
+        "    for prec in ('fp32', 'bf16'):\n"
+        "        m = make_generator(cfg, precision=prec).cuda()\n"
+        "        with torch.no_grad():\n"
+        "            y = m(torch.from_numpy(g['mel_b']).cuda()).cpu().numpy()\n"
+        "        out[prec] = [max(out[prec][0], max_abs(y, g['y_b'])), min(out[prec][1], snr_db(g['y_b'], y))]\n"
         "print(json.dumps(out))\n")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env={**os.environ, **env})
     assert r.returncode == 0, r.stderr[-2000:]

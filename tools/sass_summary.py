@@ -10,7 +10,8 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-objs = [os.path.join(ROOT, "tts_king_b200", "build", f) for f in ("conv_tc.o", "conv_pair_tc.o", "tail.o", "conv_ffma.o")]
+objs = [os.path.join(ROOT, "tts_king_b200", "build", f) for f in ("conv_tc.o", "conv_tc2.o", "conv_pair_tc.o", "conv_pair_fold.o",
+                                                                    "conv_narrow.o", "tail.o", "conv_ffma.o")]
 KEYS = ["UTCHMMA", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "SYNCS", "UTCATOM", "HMMA", "FFMA", "LDG", "STG", "LDS", "STS", "R2UR", "ELECT"]
 show = "conv_tc_kernelILi128ELi64ELi2ELb0"
 for o in objs:
