@@ -283,9 +283,12 @@ def test_forward_into_writes_only_the_window(prec):
 
 def test_profile_reports_what_each_launch_ran():
     m = make_generator(fx.V1, precision="bf16").cuda()
-    mel = fx.synthetic_mel(2, 64, seed=5).cuda()
+    # a short input runs the latency schedule: 256-channel convs in 64-column N tiles on the single-CTA kernel
+    small = {r["name"]: r for r in m.profile_layers(fx.synthetic_mel(1, 64, seed=5).cuda())}
+    assert small["resblocks.2.convs1.0"]["kernel"] == "tcgen05" and small["resblocks.2.convs1.0"]["n_tile"] == 64
+    mel = fx.synthetic_mel(8, 200, seed=5).cuda()
     rows = m.profile_layers(mel)
-    assert len(rows) == m.kernel_launches(2, 64) == 61
+    assert len(rows) == m.kernel_launches(8, 200) == 61
     assert all(r["ms"] > 0 for r in rows)
     by_name = {r["name"]: r for r in rows}
     assert by_name["mel_to_operand"]["kernel"] == "repack" and by_name["conv_post"]["kernel"] == "conv_post"

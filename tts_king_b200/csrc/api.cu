@@ -392,6 +392,22 @@ extern "C" int hg_plan_create(const HgConfig* cfg, int device, HgPlan** out) {
     }
     if (any) p->layers_pad = padded;
   }
+  // Latency schedule (BASELINE cfg-1: one 256-frame utterance): a 256-channel conv over 2 048 rows is 8 CTA-pair
+  // tiles of 256 x 256 — 16 of 148 SMs busy, each issuing the whole K loop.  With 64-column N tiles the same layer is
+  // 64 work items (16 M tiles x 4 N blocks) with a quarter of the MMAs and of the weight stream each.
+  if (env_int("HG_SMALL_TILES", 1)) {
+    bool any = false;
+    std::vector<Layer> small(p->layers.size());
+    for (size_t i = 0; i < p->layers.size(); ++i) {
+      const Layer& l = p->layers[i];
+      if (l.kind != L_CONV || !l.tc || l.n_tile != 256) continue;
+      small[i] = l;
+      small[i].n_tile = 64;
+      small[i].n_blocks = l.n_total / 64;
+      any = true;
+    }
+    if (any) p->layers_small = small;
+  }
   *out = p;
   return HG_OK;
 }
@@ -401,6 +417,8 @@ static const std::vector<Layer>& active_layers(const HgPlan* plan, int precision
   return (precision == HG_PREC_BF16 && !plan->layers_pad.empty() && !plan->force_ffma) ? plan->layers_pad : plan->layers;
 }
 static int layer_index(const HgPlan* plan, const Layer* l) {
+  if (!plan->layers_small.empty() && l >= plan->layers_small.data() && l < plan->layers_small.data() + plan->layers_small.size())
+    return static_cast<int>(l - plan->layers_small.data());
   if (!plan->layers_pad.empty() && l >= plan->layers_pad.data() && l < plan->layers_pad.data() + plan->layers_pad.size())
     return static_cast<int>(l - plan->layers_pad.data());
   return static_cast<int>(l - plan->layers.data());
@@ -534,6 +552,12 @@ extern "C" int hg_plan_upload_weight(HgPlan* plan, const char* name, const float
   DEVICE_SCOPE(plan->device);
   if (l.loaded) free_layer(l);
   int rc = pack_layer(l, weight, bias);
+  if (!rc && !plan->layers_small.empty() && plan->layers_small[it->second].tc) {
+    Layer& ls = plan->layers_small[it->second];  // the same tensors in 64-column N tiles (latency schedule)
+    if (ls.loaded) free_layer(ls);
+    ls.w_hi = ls.w_lo = nullptr; ls.w_ffma = nullptr; ls.bias = nullptr; ls.bias_fold = nullptr; ls.w_post = nullptr;
+    rc = pack_layer(ls, weight, bias);
+  }
   if (rc || plan->layers_pad.empty()) return rc;
   Layer& lp = plan->layers_pad[it->second];  // the same tensors, zero-padded, for the bf16 schedule
   if (lp.loaded) free_layer(lp);
@@ -553,6 +577,7 @@ extern "C" int hg_plan_destroy(HgPlan* plan) {
   DeviceScope scope(plan->device);
   for (auto& l : plan->layers) free_layer(l);
   for (auto& l : plan->layers_pad) free_layer(l);
+  for (auto& l : plan->layers_small) if (l.loaded) free_layer(l);
   delete plan;
   return HG_OK;
 }
@@ -658,7 +683,7 @@ static bool use_tc(const HgPlan* plan, const Layer& l, int precision) {
   return l.tc && precision != HG_PREC_FP32_FFMA && !plan->force_ffma;
 }
 
-static TcTiling choose_tiling(const HgPlan* plan, const Layer& l, bool split, int slot = 6144) {
+static TcTiling choose_tiling(const HgPlan* plan, const Layer& l, bool split, int slot = 6144, int max_ms = 0) {
   TcTiling t;
   int min_off = l.tap_off[0], max_off = l.tap_off[0];
   for (int j = 1; j < l.ntaps; ++j) {
@@ -670,6 +695,7 @@ static TcTiling choose_tiling(const HgPlan* plan, const Layer& l, bool split, in
   // two accumulator buffers of MS x N_T fp32 columns must fit the 512 TMEM columns
   int ms = l.n_tile == 256 ? 1 : l.n_tile == 128 ? 2 : l.n_tile == 64 ? 2 : 4;
   if (plan->force_ms) ms = plan->force_ms;
+  if (max_ms && ms > max_ms) ms = max_ms;
   while (2 * ms * l.n_tile > 512) ms >>= 1;
   const size_t kMaxSmem = 227 * 1024;
   const int total_stages = l.nc * l.ntaps * (split ? 2 : 1);
@@ -719,6 +745,13 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
   epi.out_offset = l.kind == L_CONVT ? -static_cast<long long>(l.pad) * l.cout : 0;
   RaggedItems rag_store;
   const RaggedItems* rag = ragged_items(&rag_store, B, L_in, rows - L_in);
+  // how many 256-row tiles the launch has: below an eighth of the SM count it is latency-, not throughput-bound
+  const bool few_tiles = static_cast<long long>(B) * ((rows + 255) / 256) * 8 <= plan->sm_count;
+  if (few_tiles && precision == HG_PREC_BF16 && !plan->layers_small.empty() && l.kind == L_CONV && l.n_tile == 256 && !plan->force_ffma) {
+    const int idx = layer_index(plan, &l);
+    if (idx >= 0 && idx < static_cast<int>(plan->layers_small.size()) && plan->layers_small[idx].loaded)
+      return run_layer(plan, plan->layers_small[idx], precision, B, L_in, in, epi, st);
+  }
   if (use_tc(plan, l, precision)) {
     const bool split = precision == HG_PREC_FP32;
     // TMA epilogue for same-length convs without MRF accumulate (68 of the 78 layers of V1); its
@@ -740,7 +773,8 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
       const int slot = slot2;  // shadows the single-CTA kernel's slot size inside this branch
       int min_off = l.tap_off[0], max_off = l.tap_off[0];
       for (int j = 1; j < l.ntaps; ++j) { min_off = std::min(min_off, l.tap_off[j]); max_off = std::max(max_off, l.tap_off[j]); }
-      const int ms = l.n_tile == 256 ? 1 : 2;
+      // two 128-row sub-tiles per CTA unless that leaves most of the GPU without a tile (short inputs)
+      const int ms = (l.n_tile == 256 || static_cast<long long>(B) * ((rows + 511) / 512) * 2 <= plan->sm_count / 2) ? 1 : 2;
       const int need = ms * 128 + (max_off - min_off);
       const int nboxes = (need + 255) / 256;
       const int box_rows = (((need + nboxes - 1) / nboxes) + 7) / 8 * 8;
@@ -777,7 +811,7 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
         return HG_OK;
       }
     }
-    TcTiling t = choose_tiling(plan, l, split, slot);
+    TcTiling t = choose_tiling(plan, l, split, slot, few_tiles ? 1 : 0);
     if (tma_epi && (t.stages < 3 && !t.resident)) {
       // the TMA epilogue's tiles squeeze the weight ring too far (fp32 split mode at 256 channels):
       // use the generic epilogue's 2 KB transpose slots instead

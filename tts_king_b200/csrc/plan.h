@@ -106,6 +106,9 @@ struct HgPlan {
   // bf16 schedule when a stage has fewer than 16 channels: the same layers with that stage's tensors padded
   // to 16 channels (zero weights / bias), so that it runs on the tensor-core kernels; empty otherwise
   std::vector<hg::Layer> layers_pad;
+  // latency schedule: the 256-channel convs again with 64-column N tiles (4 N blocks), used when a launch has too
+  // few M tiles to occupy the GPU (one short utterance); entries for other layers stay unloaded
+  std::vector<hg::Layer> layers_small;
   std::map<std::string, int> by_name;
   int desc_mode = 0;  // measured on B200 (selftest.cu): UMMA swizzle phase comes from absolute smem address bits
   int force_ms = 0, force_stages = 0;
