@@ -541,14 +541,14 @@ extern "C" int hg_plan_upload_weight(HgPlan* plan, const char* name, const float
   auto it = plan->by_name.find(name);
   if (it == plan->by_name.end()) return fail(HG_EINVAL, "unexpected key in state_dict: %s", name);
   Layer& l = plan->layers[it->second];
+  const int cin_sd = l.cin_w ? l.cin_w : l.cin, cout_sd = l.cout_w ? l.cout_w : l.cout;  // state_dict dims
   int64_t want[3];
-  if (l.kind == L_CONVT) { want[0] = l.cin; want[1] = l.cout; want[2] = l.k; }
-  else { want[0] = l.cout; want[1] = l.cin; want[2] = l.k; }
-  if (l.kind == L_POST) { want[0] = 1; want[1] = l.cin; want[2] = l.k; }
+  if (l.kind == L_CONVT) { want[0] = cin_sd; want[1] = cout_sd; want[2] = l.k; }
+  else { want[0] = cout_sd; want[1] = cin_sd; want[2] = l.k; }
   if (ndim != 3 || shape[0] != want[0] || shape[1] != want[1] || shape[2] != want[2])
     return fail(HG_EINVAL, "size mismatch for %s.weight: expected [%lld,%lld,%lld]", name,
                 static_cast<long long>(want[0]), static_cast<long long>(want[1]), static_cast<long long>(want[2]));
-  if (bias_len != l.cout) return fail(HG_EINVAL, "size mismatch for %s.bias: expected [%d]", name, l.cout);
+  if (bias_len != cout_sd) return fail(HG_EINVAL, "size mismatch for %s.bias: expected [%d]", name, cout_sd);
   DEVICE_SCOPE(plan->device);
   if (l.loaded) free_layer(l);
   int rc = pack_layer(l, weight, bias);
@@ -739,9 +739,11 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
   const long long L_out = l.kind == L_CONVT ? static_cast<long long>(L_in - 1) * l.stride - 2 * l.pad + l.k : L_in;
   epi.bias = l.bias;
   epi.a_fmt = a_fmt_of(precision);
-  epi.out_batch_stride = L_out * l.cout;
-  epi.out_extent = L_out * l.cout;
-  epi.out_row_stride = l.n_total;
+  const int c_store = l.n_store ? l.n_store : l.cout;  // width of the output tensor in memory
+  epi.out_batch_stride = L_out * c_store;
+  epi.out_extent = L_out * c_store;
+  epi.out_row_stride = l.n_store ? l.n_store : l.n_total;
+  epi.n_valid = l.n_store;
   epi.out_offset = l.kind == L_CONVT ? -static_cast<long long>(l.pad) * l.cout : 0;
   RaggedItems rag_store;
   const RaggedItems* rag = ragged_items(&rag_store, B, L_in, rows - L_in);
@@ -756,7 +758,7 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
     const bool split = precision == HG_PREC_FP32;
     // TMA epilogue for same-length convs without MRF accumulate (68 of the 78 layers of V1); its
     // per-warp slot holds the residual-in, x-out and operand-out tiles the layer actually uses
-    bool tma_epi = plan->epi_tma && l.kind == L_CONV && !epi.acc_in && epi.post_div <= 0.f && l.cout % 16 == 0;
+    bool tma_epi = plan->epi_tma && l.kind == L_CONV && !epi.acc_in && epi.post_div <= 0.f && l.cout % 16 == 0 && !l.n_store;
     int slot = 2048;  // generic epilogue: one 32x16 fp32 transpose tile per warp
     if (tma_epi) {
       slot = (epi.res ? 2048 : 0) + (epi.out_x ? 2048 : 0) + (epi.out_a0 ? (split ? 2048 : 1024) : 0);
@@ -766,7 +768,7 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
     // — whenever the single-CTA kernel could not keep the layer's weights resident in shared memory
     // (its TMA epilogue also takes the MRF running sum as a second input tile, so the last conv of a
     // ResBlock — xs += x, / num_kernels — stays on this path)
-    const bool tma_epi2 = plan->epi_tma && l.kind == L_CONV && l.cout % 16 == 0;
+    const bool tma_epi2 = plan->epi_tma && l.kind == L_CONV && l.cout % 16 == 0 && !l.n_store;
     const int slot2 = std::max(1024, (epi.res ? 2048 : 0) + (epi.acc_in ? 2048 : 0) + (epi.out_x ? 2048 : 0) + (epi.out_a0 ? 1024 : 0));
     if (plan->use_tc2 && tma_epi2 && !split && l.n_blocks == 1 && l.kc == 64 && (l.n_tile == 128 || l.n_tile == 256) &&
         !choose_tiling(plan, l, split, tma_epi ? slot : 2048).resident) {
@@ -1499,7 +1501,14 @@ extern "C" int hg_stack_create(const HgStackLayer* layers, int n_layers, int dev
   p->is_stack = true;
   init_plan_env(p, device);
   for (int i = 0; i < n_layers; ++i) {
-    p->layers.push_back(make_conv(std::to_string(i), layers[i].c_in, layers[i].c_out, layers[i].k, layers[i].dilation));
+    // an output width that is not a multiple of 32 (80 mel bins) has no tensor-core tiling: the LAST layer may run
+    // with its N padded up on zero weights, the padded columns never stored (intermediate layers would change the
+    // operand pitch of their consumer, so only the final 80-wide projection is treated this way)
+    const int co = layers[i].c_out;
+    const bool pad_n = i == n_layers - 1 && co % 32 != 0 && co >= 48 && co % 4 == 0 && env_int("HG_STACK_PAD_N", 1);
+    Layer sl = make_conv(std::to_string(i), layers[i].c_in, pad_n ? (co + 31) / 32 * 32 : co, layers[i].k, layers[i].dilation);
+    if (pad_n) { sl.cout_w = co; sl.cin_w = layers[i].c_in; sl.n_store = co; }
+    p->layers.push_back(sl);
     p->stack_act.push_back(layers[i].act);
     p->stack_slope.push_back(layers[i].slope);
     p->by_name[p->layers.back().name] = i;
@@ -1520,7 +1529,7 @@ static void layout_stack(const HgPlan* plan, int B, int T, int precision, void* 
   size_t max_a = 0, max_f = 0;
   for (const Layer& l : plan->layers) {
     max_a = std::max(max_a, static_cast<size_t>(B) * T * in_pitch(plan, l, precision));
-    max_f = std::max(max_f, static_cast<size_t>(B) * T * l.cout);
+    max_f = std::max(max_f, static_cast<size_t>(B) * T * (l.n_store ? l.n_store : l.cout));
   }
   const size_t plane = align_up(max_a * 2, 1024);
   const size_t ab = precision == HG_PREC_BF16 ? plane : precision == HG_PREC_FP32 ? 2 * plane : align_up(max_a * 4, 1024);

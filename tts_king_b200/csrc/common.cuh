@@ -78,6 +78,8 @@ struct EpiParams {
   int a_fmt;            // OperandFmt of out_a*
   float slope;          // leaky_relu slope baked into the operand copy (0.1, hifi/models.py:9)
   float post_div;       // > 0: result = (acc_in + result) / post_div                :196 xs / num_kernels
+  int n_valid;          // > 0: GEMM columns >= n_valid are computed on zero weights and not stored (an output width
+                        // padded up to the MMA's N granularity: the 80-mel layers of the FastSpeech2 tail run as N = 96)
   long long out_batch_stride;  // elements between items (= L_out*C_out)
   long long out_offset;
   long long out_extent;  // L_out*C_out
@@ -92,7 +94,7 @@ __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? 
 __device__ __forceinline__ void epilogue_vec4(const EpiParams& e, int b, long long q, int n, float v0, float v1,
                                               float v2, float v3) {
   const long long f = q * e.out_row_stride + n + e.out_offset;
-  if (f < 0 || f + 4 > e.out_extent) return;
+  if (f < 0 || f + 4 > e.out_extent || (e.n_valid > 0 && n + 4 > e.n_valid)) return;
   const long long idx = static_cast<long long>(b) * e.out_batch_stride + f;
   const float4 bb = *reinterpret_cast<const float4*>(e.bias + n);
   v0 += bb.x; v1 += bb.y; v2 += bb.z; v3 += bb.w;
@@ -152,6 +154,7 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& e, int b, long lo
   const long long f0 = q0 * e.out_row_stride + n + e.out_offset;
   const long long fstep = static_cast<long long>(row_step) * e.out_row_stride;
   const long long base = static_cast<long long>(b) * e.out_batch_stride;
+  if (e.n_valid > 0 && n + 4 > e.n_valid) return;  // a padded output column group
   bool ok[NR];
 #pragma unroll
   for (int i = 0; i < NR; ++i) {
@@ -267,10 +270,11 @@ __device__ __forceinline__ void epi_prefetch(const EpiParams& e, int b, long lon
   const long long fstep = static_cast<long long>(row_step) * e.out_row_stride;
   const long long base = static_cast<long long>(b) * e.out_batch_stride;
   okmask = 0;
+  const bool col_ok = !(e.n_valid > 0 && n + 4 > e.n_valid);
 #pragma unroll
   for (int i = 0; i < NR; ++i) {
     const long long f = f0 + i * fstep;
-    if (f >= 0 && f + 4 <= e.out_extent && q0 + static_cast<long long>(i) * row_step < q_limit) okmask |= 1u << i;
+    if (col_ok && f >= 0 && f + 4 <= e.out_extent && q0 + static_cast<long long>(i) * row_step < q_limit) okmask |= 1u << i;
   }
   if (e.res) {
     const float* rp = e.res + base + f0;
@@ -358,7 +362,7 @@ __device__ __forceinline__ void epi_finish(const EpiParams& e, int b, long long 
 // CUDA-core path).
 __device__ __forceinline__ void epilogue_scalar(const EpiParams& e, int b, long long q, int n, float v) {
   const long long f = q * e.out_row_stride + n + e.out_offset;
-  if (f < 0 || f >= e.out_extent) return;
+  if (f < 0 || f >= e.out_extent || (e.n_valid > 0 && n >= e.n_valid)) return;
   const long long idx = static_cast<long long>(b) * e.out_batch_stride + f;
   v += e.bias[n];
   if (e.res) v += e.res[idx];

@@ -26,6 +26,9 @@ struct Layer {
   // channel counts of the state_dict tensors when this layer runs zero-padded to cin / cout channels in
   // memory (the bf16 schedule of stages narrower than 16 channels); 0 = not padded
   int cin_w = 0, cout_w = 0;
+  // > 0: the output tensor is only n_store channels wide although the GEMM computes cout (zero weights beyond):
+  // conv-stack layers whose width is not a multiple of 32 (the 80-mel outputs of the FastSpeech2 tail)
+  int n_store = 0;
   // GEMM view
   int ntaps = 0;
   int tap_off[kMaxTaps] = {0};  // input row = GEMM row + tap_off
