@@ -30,6 +30,14 @@ with torch.no_grad():
             torch.cuda.synchronize()
             ok = bool(torch.isfinite(y).all()) and bool(torch.equal(yr[1, 0, :5 * m.hop_length], y[1, 0, :5 * m.hop_length]))
             print(name, prec, "ok" if ok else "MISMATCH", tuple(y.shape), tuple(yi.shape))
+    # the throughput schedule (enough tiles for the CTA-pair kernels and the 256-column N tiles); with HG_FOLD=2 in the
+    # environment every fused pair runs on the time-folded kernel, with HG_FOLD=0 on the N = C kernel
+    m = make_generator(fx.V1, precision="bf16").cuda()
+    mel = fx.synthetic_mel(2, 300, seed=9).cuda()
+    y = m(mel)
+    yr = m.forward_ragged(mel, [300, 41])
+    torch.cuda.synchronize()
+    print("v1 bf16 2x300", "ok" if bool(torch.isfinite(y).all()) and bool(torch.equal(yr[1, 0, :41 * 256], y[1, 0, :41 * 256])) else "MISMATCH")
     for prec in ("bf16", "fp32", "fp32_ffma"):
         post = PostNet(**fx.POSTNET_TINY, precision=prec).eval().cuda()
         lin = MelLinear(48, 80, precision=prec).cuda()
