@@ -240,6 +240,12 @@ HG_API int hg_op_conv_post(int device, const float* x, int B, int L, int C, cons
 HG_API int hg_op_conv_pair(int device, const float* x, int B, int L, int C, int k, int d1,
                            const float* w1, const float* b1, const float* w2, const float* b2,
                            float in_slope, const float* residual, float* y, void* stream);
+/* A whole ResBlock1 (reference hifi/models.py:88-95): np pairs, weights w1[m] / w2[m] of shape [C, C, k], first-conv
+ * dilations d1[m]; y = block(x).  Runs the fused-ResBlock kernel (csrc/conv_chain_tc.cu) when the shape is covered
+ * (C in {32, 64}, k = 3, bf16 arithmetic) and otherwise the pair kernels; `fused` (nullable) reports which. */
+HG_API int hg_op_resblock1(int device, const float* x, int B, int L, int C, int k, int np, const int32_t* d1,
+                           const float* const* w1, const float* const* b1, const float* const* w2,
+                           const float* const* b2, float slope, float* y, void* stream, int32_t* fused);
 
 /*
  * Per-layer timing (bench.py's roofline pass; the reference has no profiler).
@@ -264,7 +270,8 @@ enum {
   HG_PATH_FUSED_PAIR = 3,  /* conv_pair_tc.cu: c1 + c2 of a ResBlock pair in one launch (reported under c2's name) */
   HG_PATH_NARROW = 4,      /* conv_narrow.cu: 8 / 16 channels */
   HG_PATH_POST = 5,        /* tail.cu: conv_post + tanh (+ int16) */
-  HG_PATH_REPACK = 6       /* tail.cu: mel -> operand layout */
+  HG_PATH_REPACK = 6,      /* tail.cu: mel -> operand layout */
+  HG_PATH_FUSED_BLOCK = 7  /* conv_chain_tc.cu: a whole ResBlock1 (all pairs) in one launch (reported under its last c2) */
 };
 HG_API int hg_layer_count(const HgPlan* plan, int* count);
 /* Static description of plan layer `index`; the tiling fields are the single-CTA tcgen05 kernel's

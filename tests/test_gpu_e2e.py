@@ -363,7 +363,7 @@ def test_multi_gpu_sharding_matches_single_gpu():
         assert res[prec]["direct_p2p_store_bitwise_equal"]  # gather fused into conv_post's stores (NVLink P2P)
 
 
-@pytest.mark.parametrize("env", [{"HG_TC2": "0"}, {"HG_FUSE_PAIRS": "0"}, {"HG_EPI_TMA": "0"}, {"HG_FOLD": "0"}, {"HG_FOLD": "2"}, {"HG_PAD_NARROW": "0"},
+@pytest.mark.parametrize("env", [{"HG_TC2": "0"}, {"HG_FUSE_PAIRS": "0"}, {"HG_EPI_TMA": "0"}, {"HG_FOLD": "0"}, {"HG_FOLD": "2"}, {"HG_PAD_NARROW": "0"}, {"HG_CHAIN": "1"},
                                  {"HG_TC2": "0", "HG_FUSE_PAIRS": "0", "HG_EPI_TMA": "0"}, {"HG_FORCE_FFMA": "1"}])
 def test_alternative_kernel_paths_keep_parity(env):
     """Every layer has more than one kernel path (CTA-pair / single-CTA tcgen05, fused / unfused

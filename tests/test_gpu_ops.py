@@ -235,6 +235,58 @@ def test_fused_pair_parity(C, k, d1, n):
     assert (y.double() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
 
 
+def _run_resblock1(x, w1, b1, w2, b2, d1):
+    """hg_op_resblock1: x [B,C,L] cpu -> (y [B,C,L], fused?)"""
+    L = _native.lib()
+    dev = torch.device("cuda", 0)
+    B, C, n = x.shape
+    k, np_ = w1[0].shape[-1], len(w1)
+    xc = x.transpose(1, 2).contiguous().to(dev)
+    y = torch.full((B, n, C), float("nan"), device=dev)
+    arr = lambda ts: (ctypes.c_void_p * np_)(*[t.data_ptr() for t in ts])  # noqa: E731
+    w1c, b1c, w2c, b2c = ([t.contiguous() for t in ts] for ts in (w1, b1, w2, b2))
+    fused = ctypes.c_int32(-1)
+    _native.check(L.hg_op_resblock1(0, xc.data_ptr(), B, n, C, k, np_, (ctypes.c_int32 * np_)(*d1), arr(w1c), arr(b1c), arr(w2c),
+                                    arr(b2c), 0.1, y.data_ptr(), torch.cuda.current_stream().cuda_stream, ctypes.byref(fused)))
+    torch.cuda.synchronize()
+    return y, fused.value
+
+
+@pytest.mark.parametrize("C", [64, 32])
+@pytest.mark.parametrize("n", [1, 100, 232, 233, 464, 488, 489, 1000, 4104])
+def test_fused_resblock_parity(C, n):
+    """The fused-ResBlock kernel (conv_chain_tc.cu: the three (c1, c2) pairs of a k = 3 ResBlock1 in one launch,
+    residual stream and operand kept on chip) against the pair-by-pair schedule — bit for bit, every operation
+    happens in the same order — and against the fp64 restatement of hifi/models.py:88-95 with the kernels' operand
+    model.  Lengths straddle the 232 / 488-row output tiles."""
+    import os
+    g = torch.Generator().manual_seed(C * 100 + n)
+    k, d1 = 3, (1, 3, 5)
+    x = torch.randn(2, C, n, generator=g)
+    w1 = [torch.randn(C, C, k, generator=g) / (C * k) ** 0.5 for _ in d1]
+    w2 = [torch.randn(C, C, k, generator=g) / (C * k) ** 0.5 for _ in d1]
+    b1 = [torch.randn(C, generator=g) * 0.1 for _ in d1]
+    b2 = [torch.randn(C, generator=g) * 0.1 for _ in d1]
+    os.environ["HG_CHAIN"] = "1"  # the fused kernel is off by default (slower than the three pairs, see api.cu)
+    try:
+        y, fused = _run_resblock1(x, w1, b1, w2, b2, d1)
+    finally:
+        del os.environ["HG_CHAIN"]
+    assert fused == 1
+    y_pairs, fused0 = _run_resblock1(x, w1, b1, w2, b2, d1)
+    assert fused0 == 0
+    assert not torch.isnan(y).any()
+    assert torch.equal(y, y_pairs)
+    r = x.double()
+    for m, d in enumerate(d1):
+        a = bf16_round(F.leaky_relu(r.float(), 0.1))
+        xt = F.conv1d(a, bf16_round(w1[m]), b1[m].double(), dilation=d, padding=d)
+        xt = bf16_round(F.leaky_relu(xt.float(), 0.1))
+        r = (F.conv1d(xt, bf16_round(w2[m]), b2[m].double(), padding=1) + r).float().double()  # the stream is fp32
+    err = (y.cpu().transpose(1, 2).double() - r).abs().max().item()
+    assert err <= 4e-3 * r.abs().max().item(), err
+
+
 def test_tcgen05_descriptor_selftest():
     n, report = _native.selftest(0)
     import os

@@ -46,7 +46,7 @@ class HgFoldInfo(ctypes.Structure):
 
 
 KERNEL_PATHS = {0: "cuda-core", 1: "tcgen05", 2: "tcgen05 cta_group::2", 3: "tcgen05 fused pair", 4: "cuda-core narrow",
-                5: "conv_post", 6: "repack"}
+                5: "conv_post", 6: "repack", 7: "tcgen05 fused ResBlock"}
 
 
 class HgStackLayer(ctypes.Structure):
@@ -102,6 +102,10 @@ def lib() -> ctypes.CDLL:
     L.hg_op_conv_post.argtypes = [i, vp, i, i, i, vp, vp, vp, vp]
     L.hg_selftest_tcgen05.argtypes = [i, ctypes.c_char_p, sz]
     L.hg_op_conv_pair.argtypes = [i, vp, i, i, i, i, i, vp, vp, vp, vp, f, vp, vp, vp]
+    pp = ctypes.POINTER(vp)
+    L.hg_op_resblock1.argtypes = [i, vp, i, i, i, i, i, ctypes.POINTER(ctypes.c_int32), pp, pp, pp, pp, f, vp, vp,
+                                  ctypes.POINTER(ctypes.c_int32)]
+    L.hg_op_resblock1.restype = i
     L.hg_fold_info.argtypes = [i, i, i, i, ctypes.POINTER(HgFoldInfo)]
     L.hg_fold_info.restype = i
     L.hg_layer_count.argtypes = [vp, ctypes.POINTER(i)]

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libhifigan_b200.so")
-SOURCES = ["api.cu", "conv_tc.cu", "conv_tc2.cu", "conv_pair_tc.cu", "conv_pair_fold.cu", "conv_ffma.cu", "conv_narrow.cu", "tail.cu", "selftest.cu"]
+SOURCES = ["api.cu", "conv_tc.cu", "conv_tc2.cu", "conv_pair_tc.cu", "conv_pair_fold.cu", "conv_chain_tc.cu", "conv_ffma.cu", "conv_narrow.cu", "tail.cu", "selftest.cu"]
 HEADERS = ["common.cuh", "sm100_ptx.cuh", "plan.h", os.path.join("..", "..", "include", "hifigan_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -36,6 +36,10 @@ cudaError_t launch_conv_tc2(int n_t, int ms, const CUtensorMap* maps, const TcCo
                             cudaStream_t st);
 cudaError_t launch_conv_pair_tc(int c, const CUtensorMap& m, const CUtensorMap& mr, const TcPairParams& p, size_t smem,
                                 int grid, cudaStream_t st);
+size_t conv_chain_smem_bytes(int c, int buf_rows, int stages);
+int conv_chain_guard_rows();
+cudaError_t launch_conv_chain_tc(int c, const CUtensorMap& m, const CUtensorMap& mr, const TcChainParams& p, size_t smem,
+                                 int grid, cudaStream_t st);
 size_t conv_fold_smem_bytes(int c, int slab_phase_bytes, int xt_phase_bytes, int t_bufs, int stages);
 bool conv_fold_has_kernel(int c, int k, bool ring);
 cudaError_t launch_conv_pair_fold(int c, int k, bool ring, const CUtensorMap& m, const CUtensorMap& mr, const TcFoldParams& p,
@@ -299,6 +303,11 @@ static void init_plan_env(HgPlan* p, int device) {
   p->fuse_pairs = env_int("HG_FUSE_PAIRS", 1) != 0;
   p->fold_pairs = env_int("HG_FOLD", 1) != 0;
   p->fold_force = env_int("HG_FOLD", 1) == 2;
+  // Off by default: measured on B200 (16 x 800 frames) the fused ResBlock is SLOWER than its three fused pairs
+  // (0.96 vs 0.73 ms at C = 64, 0.88 vs 0.71 ms at C = 32; profiles/r2_resblock_fusion_experiment.md) — the twelve
+  // GEMM / epilogue steps of a tile are strictly sequential, so tensor pipe and epilogue warps never overlap, and
+  // the HBM bytes it saves (36 -> 12 per element) do not buy that back.  Kept, tested bit-for-bit, behind HG_CHAIN=1.
+  p->fuse_blocks = env_int("HG_CHAIN", 0) != 0;
   p->epi_tma = env_int("HG_EPI_TMA", 1) != 0;
   p->use_tc2 = env_int("HG_TC2", 1) != 0;
 }
@@ -1158,6 +1167,97 @@ static int run_pair_fold(HgPlan* plan, const Layer& l1, const Layer& l2, const F
 }
 
 // ------------------------------------------------------------------------------------------------
+// a whole ResBlock1 in one launch (conv_chain_tc.cu): C in {32, 64}, every conv k = 3 (any small odd k whose reach
+// fits the guard rows), bf16 mode
+struct ChainTiling {
+  int ms = 0, buf_rows = 0, box_rows = 0, nboxes = 0, r_out = 0, halo = 0, stages = 0, np = 0;
+  bool resident = false;
+  size_t smem = 0;
+};
+
+// c1 = first conv-1 layer of the block, c2 = first conv-2 layer; np pairs
+static bool chain_fusable(const HgPlan* plan, const Layer* c1, const Layer* c2, int np, int precision, ChainTiling* t) {
+  if (!plan->fuse_pairs || !plan->fuse_blocks || precision != HG_PREC_BF16 || plan->force_ffma) return false;
+  if (np < 2 || np > kChainMaxPairs) return false;
+  const int c = c1[0].cin, k = c1[0].k;
+  if ((c != 32 && c != 64) || (k & 1) == 0 || k > kMaxTaps) return false;
+  const int h2 = (k - 1) / 2, guard = conv_chain_guard_rows();
+  int halo = 0;
+  for (int m = 0; m < np; ++m) {
+    const Layer& a = c1[m];
+    const Layer& b = c2[m];
+    if (a.kind != L_CONV || b.kind != L_CONV || !a.tc || !b.tc) return false;
+    if (a.cin != c || a.cout != c || b.cin != c || b.cout != c || a.k != k || b.k != k || b.dil != 1) return false;
+    if (a.dil * h2 > guard) return false;
+    halo += (a.dil + 1) * h2;
+  }
+  t->np = np;
+  t->ms = 128 / c;
+  const int mt = t->ms * 128;
+  t->halo = halo;
+  t->r_out = mt - 2 * halo;
+  if (t->r_out * 4 < mt * 3) return false;  // keep at least 3/4 of every tile (k = 3: 232 of 256, 488 of 512)
+  const int rowb = c * 2, need = mt + 2 * guard;
+  t->nboxes = (need + 255) / 256;
+  const int align_rows = 1024 / rowb;
+  t->box_rows = (((need + t->nboxes - 1) / t->nboxes) + align_rows - 1) / align_rows * align_rows;
+  if (t->box_rows > 256) return false;
+  t->buf_rows = t->nboxes * t->box_rows;
+  const size_t kMaxSmem = 227 * 1024;
+  const int all = 2 * np * k;
+  if (conv_chain_smem_bytes(c, t->buf_rows, all) <= kMaxSmem) {
+    t->resident = true; t->stages = all;
+  } else {
+    t->resident = false;
+    int s = std::min(all - 1, 12);
+    while (s >= 3 && conv_chain_smem_bytes(c, t->buf_rows, s) > kMaxSmem) --s;
+    if (s < 3) return false;
+    t->stages = s;
+  }
+  t->smem = conv_chain_smem_bytes(c, t->buf_rows, t->stages);
+  return true;
+}
+
+static int run_chain(HgPlan* plan, const Layer* c1, const Layer* c2, const ChainTiling& t, int B, int L, const OperandBuf& in,
+                     EpiParams epi, float slope, cudaStream_t st) {
+  const int c = c1[0].cin;
+  const Layer& last = c2[t.np - 1];
+  epi.bias = last.bias;
+  epi.a_fmt = A_BF16;
+  epi.out_batch_stride = static_cast<long long>(L) * c;
+  epi.out_extent = static_cast<long long>(L) * c;
+  epi.out_row_stride = c;
+  epi.out_offset = 0;
+  TcChainParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.L = L; p.r_out = t.r_out;
+  p.tiles_per_item = (L + t.r_out - 1) / t.r_out;
+  RaggedItems rag_store;
+  p.total_work = ragged_fill(&p.rag, ragged_items(&rag_store, B, L, 0), B, L, t.r_out);
+  p.k = c1[0].k; p.np = t.np; p.halo = t.halo;
+  p.buf_rows = t.buf_rows; p.box_rows = t.box_rows; p.nboxes = t.nboxes;
+  p.stages = t.stages; p.w_resident = t.resident ? 1 : 0;
+  for (int m = 0; m < t.np; ++m) {
+    p.d1[m] = c1[m].dil;
+    p.w1[m] = c1[m].w_hi; p.w2[m] = c2[m].w_hi;
+    p.bias1[m] = c1[m].bias; p.bias2[m] = c2[m].bias;
+  }
+  p.slope = slope;
+  if (!epi.res) return fail(HG_ESTATE, "internal: fused ResBlock without a residual");
+  CUtensorMap m, mr;
+  int rc = make_operand_map(plan, in.a0, L, B, c, c, t.box_rows, &m);
+  if (rc) return rc;
+  if ((rc = make_f32_tile_map(plan, epi.res, L, B, c, &mr))) return rc;
+  epi.res = nullptr;  // the kernel keeps the residual in its TMA-loaded tile
+  p.epi = epi;
+  const int grid = std::min(p.total_work, plan->sm_count);
+  cudaError_t e = launch_conv_chain_tc(c, m, mr, p, t.smem, grid, st);
+  if (e != cudaSuccess) return fail(HG_ECUDA, "conv_chain_tc launch (%s): %s", last.name.c_str(), cudaGetErrorString(e));
+  if (g_prof) prof_mark(layer_index(plan, &last), make_rec(HG_PATH_FUSED_BLOCK, c, c, t.ms, t.stages, 2, t.resident, t.smem));
+  return HG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // workspace
 struct Workspace {
   float* F[3];
@@ -1236,7 +1336,9 @@ extern "C" int hg_forward_launches(const HgPlan* plan, int B, int T, int precisi
   if (plan->cfg.resblock_type == 1) {
     const int D = 3, U = plan->cfg.num_upsamples, K = plan->cfg.num_kernels;
     int li = 1 + U;
-    for (int i = 0; i < U * K; ++i, li += 2 * D)
+    for (int i = 0; i < U * K; ++i, li += 2 * D) {
+      ChainTiling ct;
+      if (chain_fusable(plan, &LY[li], &LY[li + D], D, precision, &ct)) { n -= 2 * D - 1; continue; }
       for (int m = 0; m < D; ++m) {
         PairTiling pt;
         FoldTiling ft;
@@ -1246,6 +1348,7 @@ extern "C" int hg_forward_launches(const HgPlan* plan, int B, int T, int precisi
             fold_fusable(plan, LY[li + m], LY[li + D + m], precision, Ls, &ft))
           --n;
       }
+    }
   }
   *launches = n;
   return HG_OK;
@@ -1302,6 +1405,29 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
     L = (L - 1) * up.stride - 2 * up.pad + up.k;
     // xs = sum_j resblocks[i*K+j](x) ; x = xs / K   :190-196
     for (int j = 0; j < K; ++j) {
+      ChainTiling ct;
+      if (c.resblock_type == 1 && chain_fusable(plan, &LY[li], &LY[li + D], D, precision, &ct)) {
+        // the whole ResBlock in one launch (conv_chain_tc.cu): x and the operand stay on chip between its pairs;
+        // its last epilogue is the last pair's, MRF combine included  :88-95, :193-196
+        EpiParams ep; memset(&ep, 0, sizeof(ep));
+        ep.res = ws.F[0]; ep.slope = slope;
+        if (j > 0) ep.acc_in = ws.F[2];
+        if (j < K - 1) {
+          ep.out_x = ws.F[2];
+        } else {
+          if (K > 1) ep.post_div = static_cast<float>(K);
+          if (last_stage) {
+            ep.out_x = ws.F[1];
+            x_final = ws.F[1];
+          } else {
+            ep.out_a0 = ws.A[1].a0; ep.out_a1 = ws.A[1].a1;
+            a_cur = 1;
+          }
+        }
+        if ((rc = run_chain(plan, &LY[li], &LY[li + D], ct, B, L, ws.A[0], ep, slope, st))) return rc;
+        li += 2 * D;
+        continue;
+      }
       int a_in = 0;          // operand of the block's running x (A0 = the shared stage input)
       const float* res = ws.F[0];
       for (int m = 0; m < D; ++m) {
@@ -1670,7 +1796,8 @@ extern "C" int hg_profile_launch_info(const HgPlan* plan, int launch, HgLayerInf
     info->kind = -1;
   }
   info->kernel_path = r.path;
-  info->tensor_core = (r.path == HG_PATH_TC || r.path == HG_PATH_TC_CTA_PAIR || r.path == HG_PATH_FUSED_PAIR) ? 1 : 0;
+  info->tensor_core = (r.path == HG_PATH_TC || r.path == HG_PATH_TC_CTA_PAIR || r.path == HG_PATH_FUSED_PAIR ||
+                       r.path == HG_PATH_FUSED_BLOCK) ? 1 : 0;
   info->n_tile = r.n_tile; info->k_chunk = r.kc; info->m_subtiles = r.ms; info->stages = r.stages;
   info->smem_bytes = static_cast<int32_t>(r.smem); info->weights_resident = r.resident; info->slab_buffers = r.nbuf;
   return HG_OK;
@@ -1808,6 +1935,75 @@ extern "C" int hg_op_conv_pair(int device, const float* x, int B, int L, int C, 
   cudaError_t es = cudaStreamSynchronize(st);
   cudaFree(a);
   free_layer(l1); free_layer(l2);
+  if (rc) return rc;
+  if (es != cudaSuccess) return fail(HG_ECUDA, "op execution failed: %s", cudaGetErrorString(es));
+  return HG_OK;
+}
+
+extern "C" int hg_op_resblock1(int device, const float* x, int B, int L, int C, int k, int np, const int32_t* d1,
+                               const float* const* w1, const float* const* b1, const float* const* w2,
+                               const float* const* b2, float slope, float* y, void* stream, int32_t* fused) {
+  if (!x || !d1 || !w1 || !b1 || !w2 || !b2 || !y) return fail(HG_EINVAL, "null argument");
+  if (B < 1 || L < 1 || k < 1 || k > kMaxTaps || np < 1 || np > kChainMaxPairs) return fail(HG_EINVAL, "bad shape");
+  int rc = check_device(device);
+  if (rc) return rc;
+  DEVICE_SCOPE(device);
+  HgPlan plan;
+  init_plan_env(&plan, device);
+  for (int m = 0; m < np; ++m) plan.layers.push_back(make_conv("op.block.c1." + std::to_string(m), C, C, k, d1[m]));
+  for (int m = 0; m < np; ++m) plan.layers.push_back(make_conv("op.block.c2." + std::to_string(m), C, C, k, 1));
+  auto cleanup = [&]() { for (auto& l : plan.layers) free_layer(l); };
+  for (int m = 0; m < np; ++m)
+    if ((rc = pack_layer(plan.layers[m], w1[m], b1[m])) || (rc = pack_layer(plan.layers[np + m], w2[m], b2[m]))) { cleanup(); return rc; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long n = static_cast<long long>(B) * L * C;
+  // scratch: operand planes a (bf16, + slack for the folded kernel's map) x2, fp32 residual stream x2
+  void* a[2] = {nullptr, nullptr};
+  float* f[2] = {nullptr, nullptr};
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaMalloc(&a[i], static_cast<size_t>(n) * 2 + 4096);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&f[i]), static_cast<size_t>(n) * 4);
+  }
+  auto release = [&]() { for (int i = 0; i < 2; ++i) { cudaFree(a[i]); cudaFree(f[i]); } cleanup(); };
+  if (e != cudaSuccess) { release(); return fail(HG_ECUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
+  e = launch_f32_to_operand(x, n, slope, A_BF16, a[0], nullptr, st);
+  if (e != cudaSuccess) { release(); return fail(HG_ECUDA, "f32_to_operand: %s", cudaGetErrorString(e)); }
+  ChainTiling ct;
+  const bool chain = chain_fusable(&plan, &plan.layers[0], &plan.layers[np], np, HG_PREC_BF16, &ct);
+  if (fused) *fused = chain ? 1 : 0;
+  if (chain) {
+    EpiParams ep; memset(&ep, 0, sizeof(ep));
+    ep.res = x; ep.out_x = y; ep.slope = slope;
+    OperandBuf in; in.a0 = a[0];
+    rc = run_chain(&plan, &plan.layers[0], &plan.layers[np], ct, B, L, in, ep, slope, st);
+  } else {
+    // pair by pair, as hg_forward schedules an unfused block: x_m in f[], operand in a[]
+    const float* res = x;
+    int cur = 0;
+    for (int m = 0; m < np && !rc; ++m) {
+      const Layer& l1 = plan.layers[m];
+      const Layer& l2 = plan.layers[np + m];
+      const bool last = m == np - 1;
+      EpiParams ep; memset(&ep, 0, sizeof(ep));
+      ep.res = res; ep.slope = slope;
+      ep.out_x = last ? y : f[m & 1];
+      if (!last) ep.out_a0 = a[cur ^ 1];
+      OperandBuf in; in.a0 = a[cur];
+      PairTiling pt;
+      FoldTiling ft;
+      if (fold_fusable(&plan, l1, l2, HG_PREC_BF16, L, &ft) && (plan.fold_force || fold_pays(&plan, l2, false)))
+        rc = run_pair_fold(&plan, l1, l2, ft, B, L, in, ep, slope, st);
+      else if (pair_fusable(&plan, l1, l2, HG_PREC_BF16, &pt))
+        rc = run_pair(&plan, l1, l2, pt, B, L, in, ep, slope, st);
+      else
+        rc = fail(HG_EINVAL, "shape not covered by the fused pair kernels");
+      res = f[m & 1];
+      cur ^= 1;
+    }
+  }
+  cudaError_t es = cudaStreamSynchronize(st);
+  release();
   if (rc) return rc;
   if (es != cudaSuccess) return fail(HG_ECUDA, "op execution failed: %s", cudaGetErrorString(es));
   return HG_OK;

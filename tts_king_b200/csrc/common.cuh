@@ -150,7 +150,8 @@ __device__ __forceinline__ float lrelu_fast(float v, float slope) { return fmaxf
 
 template <int NR, bool WITH_RES = true>
 __device__ __forceinline__ void epilogue_rows(const EpiParams& e, int b, long long q0, int row_step, int n,
-                                              float (&v)[NR][4], long long q_limit = 0x7fffffffffffffffLL) {
+                                              float (&v)[NR][4], long long q_limit = 0x7fffffffffffffffLL,
+                                              long long q_min = -0x7fffffffffffffffLL) {
   const long long f0 = q0 * e.out_row_stride + n + e.out_offset;
   const long long fstep = static_cast<long long>(row_step) * e.out_row_stride;
   const long long base = static_cast<long long>(b) * e.out_batch_stride;
@@ -158,8 +159,8 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& e, int b, long lo
   bool ok[NR];
 #pragma unroll
   for (int i = 0; i < NR; ++i) {
-    const long long f = f0 + i * fstep;
-    ok[i] = f >= 0 && f + 4 <= e.out_extent && q0 + static_cast<long long>(i) * row_step < q_limit;
+    const long long f = f0 + i * fstep, q = q0 + static_cast<long long>(i) * row_step;
+    ok[i] = f >= 0 && f + 4 <= e.out_extent && q < q_limit && q >= q_min;
   }
   const float4 bb = *reinterpret_cast<const float4*>(e.bias + n);
   if (WITH_RES && e.res) {
@@ -441,6 +442,33 @@ struct TcPairParams {
   long long* dbg;      // optional [grid][16] cycle counters (HG_TC_DEBUG_TIMING): wait breakdown
   RaggedPrefix rag;    // ragged batch: compacted tile index space (n == 0: dense)
   EpiParams epi;       // epilogue of c2
+};
+
+// ------------------------------------------------------------------ fused ResBlock (tcgen05)
+// conv_chain_tc.cu: all NP (dilated conv, conv) pairs of a ResBlock1 in one kernel; the residual stream and the
+// operand stay in shared memory between the pairs.  C in {32, 64}, small k (halo = sum of the reaches).
+constexpr int kChainMaxPairs = 3;
+struct TcChainParams {
+  int B;
+  int L;               // sequence length (rows per item)
+  int r_out;           // output rows per tile = MS*128 - 2*halo
+  int tiles_per_item;  // ceil(L / r_out)
+  int total_work;
+  int k;               // taps of every conv
+  int np;              // pairs
+  int d1[kChainMaxPairs];  // dilation of c1 of each pair (c2 has dilation 1)
+  int halo;            // rows lost on each side of a tile: sum over the pairs of (d1 + 1) * (k - 1) / 2
+  int buf_rows;        // rows of every on-chip operand buffer: guard + MS*128 + guard (rounded to 1024 bytes)
+  int box_rows, nboxes;  // TMA boxes of the input slab
+  int stages;          // weight ring depth (== 2*np*k when w_resident)
+  int w_resident;
+  const uint8_t* w1[kChainMaxPairs];  // packed swizzled tiles [tap][C rows][C] of c1 / c2 of each pair
+  const uint8_t* w2[kChainMaxPairs];
+  const float* bias1[kChainMaxPairs];  // [C]
+  const float* bias2[kChainMaxPairs];  // [C]; the last pair's is applied by the fused epilogue (epi.bias)
+  float slope;
+  RaggedPrefix rag;
+  EpiParams epi;       // epilogue of the last c2
 };
 
 // ------------------------------------------------------------------ fused ResBlock pair, time-folded (tcgen05)
