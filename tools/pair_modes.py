@@ -50,8 +50,10 @@ def main():
         for name, m in models.items():
             for _ in range(3):
                 m(mel)
-        for _ in range(ROUNDS):
-            for name, m in models.items():
+        names = list(models)
+        for rnd in range(ROUNDS):
+            for name in names[rnd % len(names):] + names[:rnd % len(names)]:  # rotate: nobody always follows the same variant
+                m = models[name]
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 for _ in range(10):

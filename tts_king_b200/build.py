@@ -23,7 +23,7 @@ HEADERS = ["common.cuh", "sm100_ptx.cuh", "plan.h", os.path.join("..", "..", "in
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
-]
+] + os.environ.get("HG_NVCC_EXTRA", "").split()  # e.g. -DHG_FOLD_DBG for tools/fold_dbg.py (then rebuild with --force)
 
 
 def _nvcc() -> str:

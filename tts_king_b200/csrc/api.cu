@@ -1153,6 +1153,7 @@ static int run_pair_fold(HgPlan* plan, const Layer& l1, const Layer& l2, const F
   if (!epi.res) return fail(HG_ESTATE, "internal: fused pair without a residual");
   (void)rowb;
   p.stages = t.stages;
+  p.dbg = env_int("HG_FOLD_DBG", 0);
   CUtensorMap m, mr;
   int rc = make_fold_slab_map(plan, in.a0, L, B, c, l1.dil, t.nb_slab, &m);
   if (rc) return rc;

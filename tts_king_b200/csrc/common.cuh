@@ -241,6 +241,52 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& e, int b, long lo
   }
 }
 
+// The tail of a fused pair's E2 (conv_pair_tc.cu, conv_pair_fold.cu), written for INSTRUCTION COUNT — those kernels'
+// epilogue warps are issue-bound (profiles/r2_pair_epilogue_issue_bound.md).  The thread holds eight float4: rows
+// 0, 4, ..., 28 of its warp item at four consecutive columns, residual already added.  `off` is the element offset of
+// row 0 (item, row and column folded into one 64-bit value by the caller), rows step by the compile-time STEP
+// elements, and row ii is stored iff 4*ii < nv (one 32-bit count instead of eight 64-bit range checks).  Same
+// arithmetic, in the same order, as epilogue_rows<8, false>.
+template <int STEP>
+__device__ __forceinline__ void epilogue_tail8(const EpiParams& e, long long off, int nv, const float4 bias, float4 (&v)[8]) {
+#pragma unroll
+  for (int ii = 0; ii < 8; ++ii) { v[ii].x += bias.x; v[ii].y += bias.y; v[ii].z += bias.z; v[ii].w += bias.w; }
+  if (e.acc_in) {  // MRF accumulate (the last pair of a ResBlock)
+    const float* ap = e.acc_in + off;
+    float4 a[8];
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii)
+      a[ii] = 4 * ii < nv ? *reinterpret_cast<const float4*>(ap + ii * STEP) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) {
+      v[ii].x = a[ii].x + v[ii].x; v[ii].y = a[ii].y + v[ii].y; v[ii].z = a[ii].z + v[ii].z; v[ii].w = a[ii].w + v[ii].w;
+    }
+  }
+  if (e.post_div > 0.f) {
+    const float d = e.post_div;
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) {
+      v[ii].x = __fdiv_rn(v[ii].x, d); v[ii].y = __fdiv_rn(v[ii].y, d);
+      v[ii].z = __fdiv_rn(v[ii].z, d); v[ii].w = __fdiv_rn(v[ii].w, d);
+    }
+  }
+  if (e.out_x) {
+    float* xp = e.out_x + off;
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii)
+      if (4 * ii < nv) *reinterpret_cast<float4*>(xp + ii * STEP) = v[ii];
+  }
+  if (e.out_a0) {  // bf16 operand copy of leaky_relu(result) (the pair kernels run in bf16 mode only)
+    __nv_bfloat16* hp = static_cast<__nv_bfloat16*>(e.out_a0) + off;
+    const float sl = e.slope;
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii)
+      if (4 * ii < nv)
+        *reinterpret_cast<uint2*>(hp + ii * STEP) =
+            pack_bf16x4(lrelu_fast(v[ii].x, sl), lrelu_fast(v[ii].y, sl), lrelu_fast(v[ii].z, sl), lrelu_fast(v[ii].w, sl));
+  }
+}
+
 // epilogue_rows for a caller that still has to fetch the residual itself, with the summation order of the
 // pair kernels' staged epilogue: (accumulator + residual) + bias.  All residual loads are issued first.
 template <int NR>
@@ -503,6 +549,7 @@ struct TcFoldParams {
   int a2_row0;         // conv 2: xt phase row of shift 0 for M row 0 (= delta / F); shift s adds s rows
   int t_bufs;          // 1 or 2 xt buffers
   int stages;          // streamed weights: ring depth (resident kernels hold all 2k blocks)
+  int dbg;             // EXPERIMENT: bit switches that drop parts of the kernel's work (timing only)
   const uint8_t* w1;   // packed swizzled tiles [tap][C rows][C]  (the Layer's w_hi)
   const uint8_t* w2;
   const float* bias1;  // [C]

@@ -62,6 +62,15 @@
 
 namespace hg {
 
+// Timing experiments (tools/fold_dbg.py; build with HG_NVCC_EXTRA=-DHG_FOLD_DBG): TcFoldParams::dbg bits drop parts
+// of the kernel's work — 1 MMAs, 2 global stores, 4 residual TMA, 8 slab TMA, 16 staging read-modify-write, 32 xt
+// stores, 64 weight streaming.  Results are wrong by construction; the shipped build compiles none of it.
+#ifdef HG_FOLD_DBG
+#define FOLD_DBG(bit) ((p.dbg & (bit)) != 0)
+#else
+#define FOLD_DBG(bit) false
+#endif
+
 constexpr int kFoldEpiWarps = 16;
 constexpr int kFoldThreads = (3 + kFoldEpiWarps) * 32;
 constexpr int kFoldZeroBytes = 1024;       // all-zero A operand of the accumulator-clearing MMA
@@ -216,7 +225,7 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
 
   if (warp == 0) {
     // ------------------------------------------------ weight producer: blocks in the order the MMA issuer needs them
-    if (lane == 0 && n_my > 0) {
+    if (lane == 0 && n_my > 0 && !(RING && FOLD_DBG(1))) {
       if (!RING) {
         for (int cv = 0; cv < 2; ++cv) {
           const uint8_t* w = cv ? p.w2 : p.w1;
@@ -231,8 +240,12 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
         auto load_conv = [&](const uint8_t* w) {
           for (int j = 0; j < K; ++j) {
             mbar_wait(&w_empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&w_full[stage], WBLK);
-            bulk_load_1d(wst + stage * WBLK, w + static_cast<size_t>(j) * WBLK, WBLK, &w_full[stage]);
+            if (FOLD_DBG(64)) {
+              mbar_arrive(&w_full[stage]);
+            } else {
+              mbar_arrive_expect_tx(&w_full[stage], WBLK);
+              bulk_load_1d(wst + stage * WBLK, w + static_cast<size_t>(j) * WBLK, WBLK, &w_full[stage]);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         };
@@ -261,8 +274,12 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
       if (lane == 0) {
         mbar_wait(&slab_empty[buf], ((i >> 1) & 1) ^ 1);
         uint64_t* bar = fix ? &slab_land[buf] : &slab_full[buf];
-        mbar_arrive_expect_tx(bar, F * box_bytes);
-        for (int h = 0; h < F; ++h) tma_load_5d(dst + h * p.slab_phase_bytes, &map_in, bar, 0, 0, h, blk_first, b);
+        if (FOLD_DBG(8)) {
+          mbar_arrive(bar);
+        } else {
+          mbar_arrive_expect_tx(bar, F * box_bytes);
+          for (int h = 0; h < F; ++h) tma_load_5d(dst + h * p.slab_phase_bytes, &map_in, bar, 0, 0, h, blk_first, b);
+        }
       }
       if (fix) {
         // rows L .. nblk_item*fdiv - 1 sit inside the tensor map's extent (they are the next item's first
@@ -305,7 +322,8 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
         mbar_wait(&d1_empty[buf], ph ^ 1);
         mbar_wait(&slab_full[buf], ph);
         tc_fence_after();
-        fold_issue_conv<C, K, RING>(tmem_base + buf * ACC_COLS, slab_lo + buf * slab_buf16, slab_phase16, a1_row0_16, a1_shift16,
+        if (!FOLD_DBG(1))
+          fold_issue_conv<C, K, RING>(tmem_base + buf * ACC_COLS, slab_lo + buf * slab_buf16, slab_phase16, a1_row0_16, a1_shift16,
                                     wst_lo, zero_lo, w_full, w_empty, ring, !w_seen1);
         umma_commit(&slab_empty[buf]);
         umma_commit(&d1_full[buf]);
@@ -319,7 +337,8 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
         mbar_wait(&t_full[tbi], tph);
         mbar_wait(&d2_empty[buf], ph ^ 1);
         tc_fence_after();
-        fold_issue_conv<C, K, RING>(tmem_base + (2 + buf) * ACC_COLS, t_lo + tbi * t_buf16, xt_phase16, a2_row0_16, a2_shift16,
+        if (!FOLD_DBG(1))
+          fold_issue_conv<C, K, RING>(tmem_base + (2 + buf) * ACC_COLS, t_lo + tbi * t_buf16, xt_phase16, a2_row0_16, a2_shift16,
                                     RING ? wst_lo : wst_lo + K * (WBLK >> 4), zero_lo, RING ? w_full : w_full + K,
                                     RING ? w_empty : w_empty + K, ring, !w_seen2);
         umma_commit(&t_empty[tbi]);
@@ -348,12 +367,28 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
     // the accumulator in descending phase order: its two 16-column halves are swapped relative to memory.
     const int c02m = (C >= 32) ? (F - 1 - c02 / C) * C + (c02 % C) : (F - (c02 + 32) / C) * C;
 
-    // E1: D1 -> (+b1, leaky_relu, bf16) -> xt phase slabs in UMMA layout; two 16-column items per warp
-    auto e1 = [&](int i) {
-      const int work = blockIdx.x + i * gridDim.x;
+    // The epilogue warps are INSTRUCTION-ISSUE bound (profiles/r2_pair_epilogue_issue_bound.md: with every MMA,
+    // global access and shared-memory transpose switched off the kernel still took 57 % of its time, 16 warps x
+    // ~1 260 SASS instructions per tile): everything below is written for instruction count — tile coordinates
+    // are decoded once per tile, shared memory is addressed through 32-bit window addresses with the swizzle
+    // folded into per-thread constants, global rows step by compile-time strides from one 64-bit base, row
+    // validity is one 32-bit count, and the biases live in registers.
+    struct TileAt { int b, g0, q0; };  // item, first xt row (global time row), first folded output row
+    auto locate = [&](int i) {
       int b, tile;
-      decode_tile(p.rag, p.tiles_per_item, work, b, tile);
-      const int g0 = tile * p.r_out - p.delta;
+      decode_tile(p.rag, p.tiles_per_item, blockIdx.x + i * gridDim.x, b, tile);
+      return TileAt{b, tile * p.r_out - p.delta, (tile * p.r_out) >> LOG2F};
+    };
+    const uint32_t tb_s = smem_u32(tbuf);
+    float* stg = staging + e * kFoldStageFloats;
+    const uint32_t stg_s = smem_u32(stg);
+    const int c4 = lane & 7, rsub = lane >> 3;
+    const int n2 = c02m + c4 * 4;
+    const int tau0 = p.fdiv * blk1 + r1;  // xt row of (this M row, phase 0), tile-relative; phase h adds h * d1
+    const float slope1 = p.slope;
+
+    // E1: D1 -> (+b1, leaky_relu, bf16) -> xt phase slabs in UMMA layout; two 16-column items per warp
+    auto e1 = [&](int i, const TileAt& at) {
       const int buf = i & 1;
       const uint32_t ph = (i >> 1) & 1;
       const int tbi = p.t_bufs == 2 ? buf : 0;
@@ -361,41 +396,41 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
       mbar_wait(&d1_full[buf], ph);
       mbar_wait(&t_empty[tbi], tph ^ 1);  // the G2 that last read this xt buffer has retired
       tc_fence_after();
-      uint8_t* tb = tbuf + tbi * t_bytes;
+      const uint32_t tbs = tb_s + tbi * t_bytes;
       const uint32_t tmem_acc = tmem_base + buf * ACC_COLS + lane_base;
 #pragma unroll 1
       for (int j = sub; j < 8; j += 4) {
         uint32_t r[16];
         tmem_ld_32x16(tmem_acc + 16 * j, r);
+        const int q = (16 * j) / C, c0 = (16 * j) % C;
+        const int tau = tau0 + (F - 1 - q) * p.d1;
+        const bool inside = static_cast<unsigned>(at.g0 + tau) < static_cast<unsigned>(p.L);
+        const float4* bp = reinterpret_cast<const float4*>(p.bias1 + c0);
+        const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1), b2 = __ldg(bp + 2), b3 = __ldg(bp + 3);
         tmem_ld_wait();
         if (j + 4 >= 8) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&d1_empty[buf]);
         }
-        const int q = (16 * j) / C, c0 = (16 * j) % C;
-        const int h = F - 1 - q;
-        const int tau = p.fdiv * blk1 + h * p.d1 + r1;  // xt row of (M row, phase h), tile-relative
-        const int grow = g0 + tau;
-        const bool inside = grow >= 0 && grow < p.L;
-        uint32_t pk[8];
-#pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
-          const float4 bb = *reinterpret_cast<const float4*>(p.bias1 + c0 + 4 * qq);
-          const float v0 = inside ? lrelu_fast(__uint_as_float(r[4 * qq]) + bb.x, p.slope) : 0.f;
-          const float v1 = inside ? lrelu_fast(__uint_as_float(r[4 * qq + 1]) + bb.y, p.slope) : 0.f;
-          const float v2 = inside ? lrelu_fast(__uint_as_float(r[4 * qq + 2]) + bb.z, p.slope) : 0.f;
-          const float v3 = inside ? lrelu_fast(__uint_as_float(r[4 * qq + 3]) + bb.w, p.slope) : 0.f;
-          const uint2 u = pack_bf16x4(v0, v1, v2, v3);
-          pk[2 * qq] = u.x; pk[2 * qq + 1] = u.y;
-        }
+        uint2 u0 = pack_bf16x4(lrelu_fast(__uint_as_float(r[0]) + b0.x, slope1), lrelu_fast(__uint_as_float(r[1]) + b0.y, slope1),
+                               lrelu_fast(__uint_as_float(r[2]) + b0.z, slope1), lrelu_fast(__uint_as_float(r[3]) + b0.w, slope1));
+        uint2 u1 = pack_bf16x4(lrelu_fast(__uint_as_float(r[4]) + b1.x, slope1), lrelu_fast(__uint_as_float(r[5]) + b1.y, slope1),
+                               lrelu_fast(__uint_as_float(r[6]) + b1.z, slope1), lrelu_fast(__uint_as_float(r[7]) + b1.w, slope1));
+        uint2 u2 = pack_bf16x4(lrelu_fast(__uint_as_float(r[8]) + b2.x, slope1), lrelu_fast(__uint_as_float(r[9]) + b2.y, slope1),
+                               lrelu_fast(__uint_as_float(r[10]) + b2.z, slope1), lrelu_fast(__uint_as_float(r[11]) + b2.w, slope1));
+        uint2 u3 = pack_bf16x4(lrelu_fast(__uint_as_float(r[12]) + b3.x, slope1), lrelu_fast(__uint_as_float(r[13]) + b3.y, slope1),
+                               lrelu_fast(__uint_as_float(r[14]) + b3.z, slope1), lrelu_fast(__uint_as_float(r[15]) + b3.w, slope1));
+        if (!inside) u0 = u1 = u2 = u3 = make_uint2(0u, 0u);  // rows outside the sequence are the conv's zero padding
         // c2 has dilation 1: xt row tau lives in phase slab tau mod F at row tau / F
         const int row = tau >> LOG2F;
         const uint32_t swz = (C == 64) ? (row & 7) : (C == 32) ? ((row >> 1) & 3) : ((row >> 2) & 1);
-        const int ch = c0 >> 3;  // first 16-byte chunk of this item within the row
-        uint8_t* rp = tb + (tau & (F - 1)) * p.xt_phase_bytes + row * ROWB;
-        *reinterpret_cast<uint4*>(rp + (((ch) ^ swz) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(rp + (((ch + 1) ^ swz) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        const uint32_t ch = c0 >> 3;  // first 16-byte chunk of this item within the row
+        const uint32_t rp = tbs + (tau & (F - 1)) * p.xt_phase_bytes + row * ROWB;
+        if (!FOLD_DBG(32)) {
+          sts128u(rp + ((ch ^ swz) << 4), u0.x, u0.y, u1.x, u1.y);
+          sts128u(rp + (((ch + 1) ^ swz) << 4), u2.x, u2.y, u3.x, u3.y);
+        }
       }
       fence_proxy_async();  // generic-proxy writes of xt -> visible to the tensor core
       __syncwarp();
@@ -406,34 +441,34 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
     // 128 fp32 = 512 contiguous bytes).  The fp32 residual tile of this warp's item is TMA-loaded into the
     // warp's 4 KB staging slot (128B-swizzled box = the staging swizzle) a whole tile ahead; the accumulator
     // row is added to it in place, and after the transpose 8 lanes cover one 128-byte row segment.
-    float* stg = staging + e * kFoldStageFloats;
-    const int c4 = lane & 7, rsub = lane >> 3;
-    const int n2 = c02m + c4 * 4;
-    auto coords = [&](int i, int& b, int& q0) {
-      const int work = blockIdx.x + i * gridDim.x;
-      int tile;
-      decode_tile(p.rag, p.tiles_per_item, work, b, tile);
-      q0 = (tile * p.r_out) >> LOG2F;
-    };
-    auto prefetch_res = [&](int i) {  // lane 0 only
-      int b, q0;
-      coords(i, b, q0);
+    auto prefetch_res = [&](const TileAt& at) {  // lane 0 only
+      if (FOLD_DBG(4)) { mbar_arrive(&res_bar[e]); return; }
       mbar_arrive_expect_tx(&res_bar[e], kFoldStageFloats * 4);
-      tma_load_3d(stg, &map_res, &res_bar[e], c02m, q0 + quarter * 32, b);
-      // the MRF running sum of the same tile (last pair of ResBlocks 1, 2 of a stage) is read by plain loads in
-      // epilogue_rows: pull its contiguous 64 KB block into L2 now so that they do not wait on HBM
+      tma_load_3d(stg, &map_res, &res_bar[e], c02m, at.q0 + quarter * 32, at.b);
+      // the MRF running sum of the same tile (last pair of ResBlocks 1, 2 of a stage) is read by plain loads
+      // below: pull its contiguous 64 KB block into L2 now so that they do not wait on HBM
       if (e == 0 && p.epi.acc_in) {
-        const long long first = static_cast<long long>(q0) * 128;
+        const long long first = static_cast<long long>(at.q0) * 128;
         const long long left = (p.epi.out_extent - first) * 4;
         if (left > 0)
-          bulk_prefetch_l2(p.epi.acc_in + static_cast<long long>(b) * p.epi.out_batch_stride + first,
+          bulk_prefetch_l2(p.epi.acc_in + static_cast<long long>(at.b) * p.epi.out_batch_stride + first,
                            static_cast<uint32_t>(left < 65536 ? left : 65536) & ~15u);
       }
     };
-    auto e2 = [&](int i) {
-      int b, q0;
-      coords(i, b, q0);
+    const float4 bias2 = __ldg(reinterpret_cast<const float4*>(p.epi.bias + n2));
+    const int rows_item = static_cast<int>(p.epi.out_extent >> 7);  // folded rows per item
+    const int rows_tile = p.r_out >> LOG2F;                          // folded rows a tile owns (the rest is halo)
+    // lane-per-row view of the slot (the TMEM register layout) and its transpose (8 lanes per 128-byte row segment)
+    const uint32_t row_s = stg_s + lane * 128, x7 = static_cast<uint32_t>(lane & 7) << 4;
+    const uint32_t tr0_s = stg_s + rsub * 128 + ((c4 ^ rsub) << 4);               // rows rsub, rsub + 8, ...
+    const uint32_t tr1_s = stg_s + (rsub + 4) * 128 + ((c4 ^ (rsub + 4)) << 4);   // rows rsub + 4, rsub + 12, ...
+    auto e2 = [&](int i, const TileAt& at, const TileAt* next) {
       const int buf = i & 1;
+      // rows 4*ii + rsub (ii = 0..7) of this warp's 32: valid while inside the tile's own rows and the item
+      int nv = (rows_tile < rows_item - at.q0 ? rows_tile : rows_item - at.q0) - (quarter * 32 + rsub);
+      if (FOLD_DBG(2)) nv = 0;
+      const long long off = static_cast<long long>(at.b) * p.epi.out_batch_stride +
+                            (static_cast<long long>(at.q0 + quarter * 32 + rsub) << 7) + n2;
       mbar_wait(&d2_full[buf], (i >> 1) & 1);
       tc_fence_after();
       {
@@ -444,37 +479,40 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
         __syncwarp();
         if (lane == 0) mbar_arrive(&d2_empty[buf]);
         mbar_wait(&res_bar[e], i & 1);
+        if (!FOLD_DBG(16))
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
-          float4* sp = reinterpret_cast<float4*>(stg + lane * 32 + ((k4 ^ (lane & 7)) << 2));
-          float4 t = *sp;
+          const uint32_t a = row_s + ((k4 << 4) ^ x7);
+          float4 t = lds128(a);
           const int ka = (C >= 32) ? k4 : (k4 ^ 4);  // accumulator float4 that belongs to memory float4 k4
           t.x += __uint_as_float(r[4 * ka]); t.y += __uint_as_float(r[4 * ka + 1]);
           t.z += __uint_as_float(r[4 * ka + 2]); t.w += __uint_as_float(r[4 * ka + 3]);
-          *sp = t;
+          sts128(a, t);
         }
       }
       __syncwarp();
-      float v[8][4];
+      float4 v[8];
 #pragma unroll
-      for (int ii = 0; ii < 8; ++ii) {
-        const int row = ii * 4 + rsub;
-        const float4 t4 = *reinterpret_cast<const float4*>(stg + row * 32 + ((c4 ^ (row & 7)) << 2));
-        v[ii][0] = t4.x; v[ii][1] = t4.y; v[ii][2] = t4.z; v[ii][3] = t4.w;
-      }
+      for (int ii = 0; ii < 8; ++ii) v[ii] = lds128(((ii & 1) ? tr1_s : tr0_s) + (ii >> 1) * 1024);
       fence_proxy_async();  // our generic reads of the slot happen-before the next TMA write into it
       __syncwarp();
-      if (lane == 0 && i + 1 < n_my) prefetch_res(i + 1);
-      epilogue_rows<8, false>(p.epi, b, static_cast<long long>(q0) + quarter * 32 + rsub, 4, n2, v,
-                              static_cast<long long>(q0) + (p.r_out >> LOG2F));
+      if (lane == 0 && next) prefetch_res(*next);
+      epilogue_tail8<512>(p.epi, off, nv, bias2, v);
     };
     if (n_my > 0) {
-      if (lane == 0) prefetch_res(0);
-      e1(0);
-    }
-    for (int i = 0; i < n_my; ++i) {
-      if (i + 1 < n_my) e1(i + 1);
-      e2(i);
+      TileAt cur = locate(0);
+      if (lane == 0) prefetch_res(cur);
+      e1(0, cur);
+      for (int i = 0; i < n_my; ++i) {
+        TileAt nxt = cur;
+        const bool more = i + 1 < n_my;
+        if (more) {
+          nxt = locate(i + 1);
+          e1(i + 1, nxt);
+        }
+        e2(i, cur, more ? &nxt : nullptr);
+        cur = nxt;
+      }
     }
   }
 

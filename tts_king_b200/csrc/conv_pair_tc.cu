@@ -238,12 +238,22 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
       else mbar_wait(bar, ph);
     };
 
-    // E1: D1 -> (+b1, leaky_relu, bf16) -> xt tile in UMMA layout; two (sub-tile, 16-column) items
-    auto e1 = [&](int i) {
-      const int work = blockIdx.x + i * gridDim.x;
+    // The epilogue warps are INSTRUCTION-ISSUE bound (profiles/r2_pair_epilogue_issue_bound.md), so this code is
+    // written for instruction count: tile coordinates are decoded once per tile, shared memory is addressed through
+    // 32-bit window addresses with the swizzle folded into per-thread constants, global rows step by compile-time
+    // strides from one 64-bit base, row validity is one 32-bit count, and the c2 bias lives in registers.
+    struct TileAt { int b, m0; };  // item, first output row
+    auto locate = [&](int i) {
       int b, tile;
-      decode_tile(p.rag, p.tiles_per_item, work, b, tile);
-      const int m0 = tile * p.r_out;
+      decode_tile(p.rag, p.tiles_per_item, blockIdx.x + i * gridDim.x, b, tile);
+      return TileAt{b, tile * p.r_out};
+    };
+    const uint32_t tb_s = smem_u32(tbuf);
+    const uint32_t stg_s = smem_u32(stg);
+    const float slope1 = p.slope;
+
+    // E1: D1 -> (+b1, leaky_relu, bf16) -> xt tile in UMMA layout; two (sub-tile, 16-column) items
+    auto e1 = [&](int i, const TileAt& at) {
       const int buf = i & 1;
       const uint32_t ph = (i >> 1) & 1;
       const int tbi = p.t_bufs == 2 ? buf : 0;
@@ -252,7 +262,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
       timed_wait(&t_empty[tbi], tph ^ 1, 10);  // the G2 that last read this xt buffer has retired
       tc_fence_after();
       const long long c_s = (DBG && dbg) ? clock64() : 0;
-      uint8_t* tb = tbuf + tbi * t_bytes;
+      const uint32_t tbs = tb_s + tbi * t_bytes;
       const uint32_t tmem_acc = tmem_base + buf * ACC_COLS + lane_base;
       constexpr int ITEMS = MS * (N_T / 16);
 #pragma unroll 1
@@ -260,31 +270,30 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
         const int ms = j / (N_T / 16), c0 = (j - ms * (N_T / 16)) * 16;
         uint32_t r[16];
         tmem_ld_32x16(tmem_acc + ms * N_T + c0, r);
+        const int row = ms * 128 + quarter * 32 + lane;  // row of the xt tile; global time index m0 - h2 + row
+        const bool inside = static_cast<unsigned>(at.m0 - h2 + row) < static_cast<unsigned>(p.L);
+        const float4* bp = reinterpret_cast<const float4*>(p.bias1 + c0);
+        const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1), b2 = __ldg(bp + 2), b3 = __ldg(bp + 3);
         tmem_ld_wait();
         if (j + 4 >= ITEMS) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&d1_empty[buf]);
         }
-        const int row = ms * 128 + quarter * 32 + lane;  // row of the xt tile
-        const int grow = m0 - h2 + row;                  // global time index of that row
-        const bool inside = grow >= 0 && grow < p.L;
-        uint32_t pk[8];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 bb = *reinterpret_cast<const float4*>(p.bias1 + c0 + 4 * q);
-          const float v0 = inside ? lrelu_fast(__uint_as_float(r[4 * q]) + bb.x, p.slope) : 0.f;
-          const float v1 = inside ? lrelu_fast(__uint_as_float(r[4 * q + 1]) + bb.y, p.slope) : 0.f;
-          const float v2 = inside ? lrelu_fast(__uint_as_float(r[4 * q + 2]) + bb.z, p.slope) : 0.f;
-          const float v3 = inside ? lrelu_fast(__uint_as_float(r[4 * q + 3]) + bb.w, p.slope) : 0.f;
-          const uint2 u = pack_bf16x4(v0, v1, v2, v3);
-          pk[2 * q] = u.x; pk[2 * q + 1] = u.y;
-        }
+        uint2 u0 = pack_bf16x4(lrelu_fast(__uint_as_float(r[0]) + b0.x, slope1), lrelu_fast(__uint_as_float(r[1]) + b0.y, slope1),
+                               lrelu_fast(__uint_as_float(r[2]) + b0.z, slope1), lrelu_fast(__uint_as_float(r[3]) + b0.w, slope1));
+        uint2 u1 = pack_bf16x4(lrelu_fast(__uint_as_float(r[4]) + b1.x, slope1), lrelu_fast(__uint_as_float(r[5]) + b1.y, slope1),
+                               lrelu_fast(__uint_as_float(r[6]) + b1.z, slope1), lrelu_fast(__uint_as_float(r[7]) + b1.w, slope1));
+        uint2 u2 = pack_bf16x4(lrelu_fast(__uint_as_float(r[8]) + b2.x, slope1), lrelu_fast(__uint_as_float(r[9]) + b2.y, slope1),
+                               lrelu_fast(__uint_as_float(r[10]) + b2.z, slope1), lrelu_fast(__uint_as_float(r[11]) + b2.w, slope1));
+        uint2 u3 = pack_bf16x4(lrelu_fast(__uint_as_float(r[12]) + b3.x, slope1), lrelu_fast(__uint_as_float(r[13]) + b3.y, slope1),
+                               lrelu_fast(__uint_as_float(r[14]) + b3.z, slope1), lrelu_fast(__uint_as_float(r[15]) + b3.w, slope1));
+        if (!inside) u0 = u1 = u2 = u3 = make_uint2(0u, 0u);  // rows outside the sequence are the conv's zero padding
         const uint32_t swz = (KC == 64) ? (row & 7) : ((row >> 1) & 3);
-        const int ch = c0 >> 3;  // first 16-byte chunk of this item within the row
-        uint8_t* rp = tb + row * ROWB;
-        *reinterpret_cast<uint4*>(rp + (((ch) ^ swz) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(rp + (((ch + 1) ^ swz) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        const uint32_t ch = c0 >> 3;  // first 16-byte chunk of this item within the row
+        const uint32_t rp = tbs + row * ROWB;
+        sts128u(rp + ((ch ^ swz) << 4), u0.x, u0.y, u1.x, u1.y);
+        sts128u(rp + (((ch + 1) ^ swz) << 4), u2.x, u2.y, u3.x, u3.y);
       }
       fence_proxy_async();  // generic-proxy writes of xt -> visible to the tensor core
       __syncwarp();
@@ -296,33 +305,33 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
     // warp's item is TMA-loaded straight into the warp's 4 KB staging slot (128B-swizzled box = the
     // staging swizzle) a whole tile ahead, so no thread ever waits on a global load: the accumulator
     // row is added to it in place, and after the transpose 8 lanes cover one 128-byte row segment.
-    auto coords = [&](int i, int& b, int& m0) {
-      const int work = blockIdx.x + i * gridDim.x;
-      int tile;
-      decode_tile(p.rag, p.tiles_per_item, work, b, tile);
-      m0 = tile * p.r_out;
-    };
-    auto prefetch_res = [&](int i) {  // lane 0 only
-      int b, m0;
-      coords(i, b, m0);
+    auto prefetch_res = [&](const TileAt& at) {  // lane 0 only
       mbar_arrive_expect_tx(&res_bar[e], kPairStageFloats * 4);
-      tma_load_3d(stg, &map_res, &res_bar[e], c02, m0 + ms2 * 128 + quarter * 32, b);
-      // the MRF running sum of the same tile is read by plain loads in epilogue_rows: pull its contiguous block
+      tma_load_3d(stg, &map_res, &res_bar[e], c02, at.m0 + ms2 * 128 + quarter * 32, at.b);
+      // the MRF running sum of the same tile is read by plain loads in the tail: pull its contiguous block
       // (r_out rows x C fp32) into L2 a tile ahead so that they do not wait on HBM
       if (e == 0 && p.epi.acc_in) {
-        const long long first = static_cast<long long>(m0) * C;
+        const long long first = static_cast<long long>(at.m0) * C;
         long long left = (p.epi.out_extent - first) * 4;
         const long long want = static_cast<long long>(p.r_out) * C * 4;
         if (left > want) left = want;
         if (left > 0)
-          bulk_prefetch_l2(p.epi.acc_in + static_cast<long long>(b) * p.epi.out_batch_stride + first,
+          bulk_prefetch_l2(p.epi.acc_in + static_cast<long long>(at.b) * p.epi.out_batch_stride + first,
                            static_cast<uint32_t>(left) & ~15u);
       }
     };
-    auto e2 = [&](int i) {
-      int b, m0;
-      coords(i, b, m0);
+    const float4 bias2 = __ldg(reinterpret_cast<const float4*>(p.epi.bias + n2));
+    // lane-per-row view of the slot (the TMEM register layout) and its transpose (8 lanes per 128-byte row segment)
+    const uint32_t row_s = stg_s + lane * 128, x7 = static_cast<uint32_t>(lane & 7) << 4;
+    const uint32_t tr0_s = stg_s + rsub * 128 + ((c4 ^ rsub) << 4);               // rows rsub, rsub + 8, ...
+    const uint32_t tr1_s = stg_s + (rsub + 4) * 128 + ((c4 ^ (rsub + 4)) << 4);   // rows rsub + 4, rsub + 12, ...
+    const int row2 = ms2 * 128 + quarter * 32 + rsub;  // this thread's first row within the tile
+    auto e2 = [&](int i, const TileAt& at, const TileAt* next) {
       const int buf = i & 1;
+      // rows row2 + 4*ii (ii = 0..7): stored while inside the tile's own r_out rows and the sequence
+      const int nv = (p.r_out < p.L - at.m0 ? p.r_out : p.L - at.m0) - row2;
+      const long long off = static_cast<long long>(at.b) * p.epi.out_batch_stride +
+                            static_cast<long long>(at.m0 + row2) * C + n2;
       timed_wait(&d2_full[buf], (i >> 1) & 1, 11);
       tc_fence_after();
       const long long c_s = (DBG && dbg) ? clock64() : 0;
@@ -336,35 +345,37 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
         timed_wait(&res_bar[e], i & 1, 12);
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
-          float4* sp = reinterpret_cast<float4*>(stg + lane * 32 + ((k4 ^ (lane & 7)) << 2));
-          float4 t = *sp;
+          const uint32_t a = row_s + ((k4 << 4) ^ x7);
+          float4 t = lds128(a);
           t.x += __uint_as_float(r[4 * k4]); t.y += __uint_as_float(r[4 * k4 + 1]);
           t.z += __uint_as_float(r[4 * k4 + 2]); t.w += __uint_as_float(r[4 * k4 + 3]);
-          *sp = t;
+          sts128(a, t);
         }
       }
       __syncwarp();
-      float v[8][4];
+      float4 v[8];
 #pragma unroll
-      for (int ii = 0; ii < 8; ++ii) {
-        const int row = ii * 4 + rsub;
-        const float4 t4 = *reinterpret_cast<const float4*>(stg + row * 32 + ((c4 ^ (row & 7)) << 2));
-        v[ii][0] = t4.x; v[ii][1] = t4.y; v[ii][2] = t4.z; v[ii][3] = t4.w;
-      }
+      for (int ii = 0; ii < 8; ++ii) v[ii] = lds128(((ii & 1) ? tr1_s : tr0_s) + (ii >> 1) * 1024);
       fence_proxy_async();  // our generic reads of the slot happen-before the next TMA write into it
       __syncwarp();
-      if (lane == 0 && i + 1 < n_my) prefetch_res(i + 1);
-      epilogue_rows<8, false>(p.epi, b, static_cast<long long>(m0) + ms2 * 128 + quarter * 32 + rsub, 4, n2, v,
-                       static_cast<long long>(m0) + p.r_out);
+      if (lane == 0 && next) prefetch_res(*next);
+      epilogue_tail8<4 * C>(p.epi, off, nv, bias2, v);
       if (DBG && dbg && lane == 0) dbg[14] += clock64() - c_s;
     };
     if (n_my > 0) {
-      if (lane == 0) prefetch_res(0);
-      e1(0);
-    }
-    for (int i = 0; i < n_my; ++i) {
-      if (i + 1 < n_my) e1(i + 1);
-      e2(i);
+      TileAt cur = locate(0);
+      if (lane == 0) prefetch_res(cur);
+      e1(0, cur);
+      for (int i = 0; i < n_my; ++i) {
+        TileAt nxt = cur;
+        const bool more = i + 1 < n_my;
+        if (more) {
+          nxt = locate(i + 1);
+          e1(i + 1, nxt);
+        }
+        e2(i, cur, more ? &nxt : nullptr);
+        cur = nxt;
+      }
     }
     if (DBG && dbg && lane == 0) dbg[8] = clock64() - c_t0;
   }
