@@ -241,6 +241,38 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& e, int b, long lo
   }
 }
 
+// Packed fp32 pairs (FADD2 / FMUL2 on sm_100): one issue slot for two IEEE round-to-nearest operations — the same
+// bits as the scalar forms, half the instructions in the issue-bound pair epilogues.
+__device__ __forceinline__ float2 add_f32x2(float2 a, float2 b) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 mul_f32x2(float2 a, float2 b) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float4 add4(float4 a, float4 b) {  // a + b, operand order kept
+  const float2 lo = add_f32x2(make_float2(a.x, a.y), make_float2(b.x, b.y));
+  const float2 hi = add_f32x2(make_float2(a.z, a.w), make_float2(b.z, b.w));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+// bf16x4 of leaky_relu(v) for 0 <= slope <= 1 (lrelu_fast on four values)
+__device__ __forceinline__ uint2 lrelu_pack4(float4 v, float slope) {
+  const float2 sl = make_float2(slope, slope);
+  const float2 lo = mul_f32x2(make_float2(v.x, v.y), sl), hi = mul_f32x2(make_float2(v.z, v.w), sl);
+  return pack_bf16x4(fmaxf(v.x, lo.x), fmaxf(v.y, lo.y), fmaxf(v.z, hi.x), fmaxf(v.w, hi.y));
+}
+
 // The tail of a fused pair's E2 (conv_pair_tc.cu, conv_pair_fold.cu), written for INSTRUCTION COUNT — those kernels'
 // epilogue warps are issue-bound (profiles/r2_pair_epilogue_issue_bound.md).  The thread holds eight float4: rows
 // 0, 4, ..., 28 of its warp item at four consecutive columns, residual already added.  `off` is the element offset of
@@ -250,7 +282,7 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& e, int b, long lo
 template <int STEP>
 __device__ __forceinline__ void epilogue_tail8(const EpiParams& e, long long off, int nv, const float4 bias, float4 (&v)[8]) {
 #pragma unroll
-  for (int ii = 0; ii < 8; ++ii) { v[ii].x += bias.x; v[ii].y += bias.y; v[ii].z += bias.z; v[ii].w += bias.w; }
+  for (int ii = 0; ii < 8; ++ii) v[ii] = add4(v[ii], bias);
   if (e.acc_in) {  // MRF accumulate (the last pair of a ResBlock)
     const float* ap = e.acc_in + off;
     float4 a[8];
@@ -258,9 +290,7 @@ __device__ __forceinline__ void epilogue_tail8(const EpiParams& e, long long off
     for (int ii = 0; ii < 8; ++ii)
       a[ii] = 4 * ii < nv ? *reinterpret_cast<const float4*>(ap + ii * STEP) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int ii = 0; ii < 8; ++ii) {
-      v[ii].x = a[ii].x + v[ii].x; v[ii].y = a[ii].y + v[ii].y; v[ii].z = a[ii].z + v[ii].z; v[ii].w = a[ii].w + v[ii].w;
-    }
+    for (int ii = 0; ii < 8; ++ii) v[ii] = add4(a[ii], v[ii]);
   }
   if (e.post_div > 0.f) {
     const float d = e.post_div;
@@ -282,8 +312,7 @@ __device__ __forceinline__ void epilogue_tail8(const EpiParams& e, long long off
 #pragma unroll
     for (int ii = 0; ii < 8; ++ii)
       if (4 * ii < nv)
-        *reinterpret_cast<uint2*>(hp + ii * STEP) =
-            pack_bf16x4(lrelu_fast(v[ii].x, sl), lrelu_fast(v[ii].y, sl), lrelu_fast(v[ii].z, sl), lrelu_fast(v[ii].w, sl));
+        *reinterpret_cast<uint2*>(hp + ii * STEP) = lrelu_pack4(v[ii], sl);
   }
 }
 

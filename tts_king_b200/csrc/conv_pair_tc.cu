@@ -280,14 +280,11 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
           __syncwarp();
           if (lane == 0) mbar_arrive(&d1_empty[buf]);
         }
-        uint2 u0 = pack_bf16x4(lrelu_fast(__uint_as_float(r[0]) + b0.x, slope1), lrelu_fast(__uint_as_float(r[1]) + b0.y, slope1),
-                               lrelu_fast(__uint_as_float(r[2]) + b0.z, slope1), lrelu_fast(__uint_as_float(r[3]) + b0.w, slope1));
-        uint2 u1 = pack_bf16x4(lrelu_fast(__uint_as_float(r[4]) + b1.x, slope1), lrelu_fast(__uint_as_float(r[5]) + b1.y, slope1),
-                               lrelu_fast(__uint_as_float(r[6]) + b1.z, slope1), lrelu_fast(__uint_as_float(r[7]) + b1.w, slope1));
-        uint2 u2 = pack_bf16x4(lrelu_fast(__uint_as_float(r[8]) + b2.x, slope1), lrelu_fast(__uint_as_float(r[9]) + b2.y, slope1),
-                               lrelu_fast(__uint_as_float(r[10]) + b2.z, slope1), lrelu_fast(__uint_as_float(r[11]) + b2.w, slope1));
-        uint2 u3 = pack_bf16x4(lrelu_fast(__uint_as_float(r[12]) + b3.x, slope1), lrelu_fast(__uint_as_float(r[13]) + b3.y, slope1),
-                               lrelu_fast(__uint_as_float(r[14]) + b3.z, slope1), lrelu_fast(__uint_as_float(r[15]) + b3.w, slope1));
+        auto item4 = [&](int q, const float4 bb) {  // bf16x4 of leaky_relu(acc + bias)
+          return lrelu_pack4(add4(make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                                              __uint_as_float(r[4 * q + 3])), bb), slope1);
+        };
+        uint2 u0 = item4(0, b0), u1 = item4(1, b1), u2 = item4(2, b2), u3 = item4(3, b3);
         if (!inside) u0 = u1 = u2 = u3 = make_uint2(0u, 0u);  // rows outside the sequence are the conv's zero padding
         const uint32_t swz = (KC == 64) ? (row & 7) : ((row >> 1) & 3);
         const uint32_t ch = c0 >> 3;  // first 16-byte chunk of this item within the row
@@ -347,8 +344,8 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
         for (int k4 = 0; k4 < 8; ++k4) {
           const uint32_t a = row_s + ((k4 << 4) ^ x7);
           float4 t = lds128(a);
-          t.x += __uint_as_float(r[4 * k4]); t.y += __uint_as_float(r[4 * k4 + 1]);
-          t.z += __uint_as_float(r[4 * k4 + 2]); t.w += __uint_as_float(r[4 * k4 + 3]);
+          t = add4(t, make_float4(__uint_as_float(r[4 * k4]), __uint_as_float(r[4 * k4 + 1]), __uint_as_float(r[4 * k4 + 2]),
+                                  __uint_as_float(r[4 * k4 + 3])));
           sts128(a, t);
         }
       }
