@@ -41,8 +41,9 @@ int conv_chain_guard_rows();
 cudaError_t launch_conv_chain_tc(int c, const CUtensorMap& m, const CUtensorMap& mr, const TcChainParams& p, size_t smem,
                                  int grid, cudaStream_t st);
 size_t conv_fold_smem_bytes(int c, int slab_phase_bytes, int xt_phase_bytes, int t_bufs, int stages);
-bool conv_fold_has_kernel(int c, int k, bool ring);
-cudaError_t launch_conv_pair_fold(int c, int k, bool ring, const CUtensorMap& m, const CUtensorMap& mr, const TcFoldParams& p,
+bool conv_fold_has_kernel(int c, int k, int ring_period);
+int conv_fold_weight_slots(int k, int ring_period);
+cudaError_t launch_conv_pair_fold(int c, int k, int ring_period, const CUtensorMap& m, const CUtensorMap& mr, const TcFoldParams& p,
                                   size_t smem, int grid, cudaStream_t st);
 }  // namespace hg
 
@@ -1026,12 +1027,12 @@ static int run_pair(HgPlan* plan, const Layer& l1, const Layer& l2, const PairTi
 // the same pair with F = 128 / C time rows folded into N (conv_pair_fold.cu)
 struct FoldTiling {
   int f = 0, c_half = 0, smin = 0, smax = 0, nb_slab = 0, slab_phase_bytes = 0, xt_phase_bytes = 0, delta = 0, r_out = 0, fdiv = 0;
-  int t_bufs = 1, stages = 0;
+  int t_bufs = 1, stages = 0;  // stages: weight blocks held in shared memory
+  int ring_period = 0;         // streamed weights: period of the ring (kernel template parameter); 0 = resident
   bool resident = false;
   size_t smem = 0;
 };
 
-// pure geometry (no device state): also what hg_fold_info reports, so the CPU tests can replay the dataflow
 // pure geometry (no device state): also what hg_fold_info reports, so the CPU tests can replay the dataflow
 static bool fold_geometry(int c, int k, int d1, int L, FoldTiling* t) {
   if (c != 16 && c != 32 && c != 64) return false;
@@ -1059,7 +1060,8 @@ static bool fold_geometry(int c, int k, int d1, int L, FoldTiling* t) {
   // as fits (at least F + 2 stages: a group holds F blocks while the next ones arrive)
   const size_t kMaxSmem = 227 * 1024;
   t->stages = 0;
-  if (conv_fold_has_kernel(c, k, false)) {
+  t->ring_period = 0;
+  if (conv_fold_has_kernel(c, k, 0)) {
     for (int tb : {2, 1}) {
       if (conv_fold_smem_bytes(c, t->slab_phase_bytes, t->xt_phase_bytes, tb, 2 * k) <= kMaxSmem) {
         t->resident = true; t->stages = 2 * k; t->t_bufs = tb;
@@ -1067,27 +1069,30 @@ static bool fold_geometry(int c, int k, int d1, int L, FoldTiling* t) {
       }
     }
   }
-  if (!t->stages && conv_fold_has_kernel(c, k, true)) {
-    t->resident = false;
-    t->t_bufs = 1;
-    int s = 2 * k - 1;
-    while (s >= f + 2 && conv_fold_smem_bytes(c, t->slab_phase_bytes, t->xt_phase_bytes, 1, s) > kMaxSmem) --s;
-    if (s >= f + 2) t->stages = s;
+  if (!t->stages) {  // streamed: the longest ring period (a kernel template parameter) whose blocks fit
+    for (int s : {k, 6, 5, 4}) {
+      if (!conv_fold_has_kernel(c, k, s)) continue;
+      const int slots = conv_fold_weight_slots(k, s);
+      if (conv_fold_smem_bytes(c, t->slab_phase_bytes, t->xt_phase_bytes, 1, slots) > kMaxSmem) continue;
+      t->resident = false; t->t_bufs = 1; t->stages = slots; t->ring_period = s;
+      break;
+    }
   }
   if (!t->stages) return false;
   t->smem = conv_fold_smem_bytes(c, t->slab_phase_bytes, t->xt_phase_bytes, t->t_bufs, t->stages);
   return true;
 }
 
-// Where the time-folded kernel is the faster of the two pair kernels (A/B on B200, 16 x 800 frames,
-// profiles/r2_pair_kernel_ab.md): it wins where the N = C kernel is bound by MMA operand fetch — 32 channels
-// from k = 5 up (0.40 -> 0.28 ms at k = 11) and 64 channels at k >= 9 — and loses a few percent where the pair
-// is HBM-bound (k = 3) or when the epilogue also reads the MRF running sum with plain loads (its smaller output
-// tiles mean more of those epilogues).  HG_FOLD=2 forces it wherever it applies (tests, A/B).
+// Where the time-folded kernel is the faster of the two pair kernels (interleaved A/B on B200, 16 x 800 frames,
+// tools/pair_modes.py, profiles/r2_v10_pair_kernel_ab.txt): it wins where the N = C kernel is bound by MMA operand
+// fetch — 32 channels from k = 5 up (0.43 -> 0.28 ms at k = 11) and 64 channels from k = 7 up (0.34 -> 0.31 ms at
+// k = 7, 0.52 -> 0.38-0.44 ms at k = 11) — and loses a few percent where the pair is HBM-bound (k = 3), and at
+// k >= 9 when the epilogue also reads the MRF running sum (the last pair of a stage: its dilation-5 slab leaves the
+// shallowest weight ring).  HG_FOLD=2 forces it wherever it applies (tests, A/B).
 static bool fold_pays(const HgPlan* plan, const Layer& l2, bool mrf_accumulate) {
   if (plan->fold_force || l2.cin == 16) return true;  // 16 channels: the alternative is the CUDA-core kernel
   if (l2.cin == 32) return l2.k >= 5 && !(mrf_accumulate && l2.k >= 9);
-  return l2.k >= 9 && !mrf_accumulate;
+  return l2.k >= 7 && !(mrf_accumulate && l2.k >= 9);
 }
 
 static bool fold_fusable(const HgPlan* plan, const Layer& l1, const Layer& l2, int precision, int L, FoldTiling* t) {
@@ -1161,7 +1166,7 @@ static int run_pair_fold(HgPlan* plan, const Layer& l1, const Layer& l2, const F
   epi.res = nullptr;  // the kernel adds the residual from its TMA-loaded tile
   p.epi = epi;
   const int grid = std::min(p.total_work, plan->sm_count);
-  cudaError_t e = launch_conv_pair_fold(c, l1.k, !t.resident, m, mr, p, t.smem, grid, st);
+  cudaError_t e = launch_conv_pair_fold(c, l1.k, t.ring_period, m, mr, p, t.smem, grid, st);
   if (e != cudaSuccess) return fail(HG_ECUDA, "conv_pair_fold launch (%s): %s", l2.name.c_str(), cudaGetErrorString(e));
   if (g_prof) prof_mark(layer_index(plan, &l2), make_rec(HG_PATH_FUSED_PAIR, 128, c, 1, t.stages, 2, t.resident, t.smem));
   return HG_OK;

@@ -80,13 +80,23 @@ __host__ __device__ constexpr int fold_floor_div(int a, int b) { return a >= 0 ?
 __host__ __device__ constexpr int fold_min(int a, int b) { return a < b ? a : b; }
 __host__ __device__ constexpr int fold_max(int a, int b) { return a > b ? a : b; }
 
-// Streamed-weight ring state of the issuing thread (RING kernels).  Blocks are numbered along the conv
-// sequence G1(0) G1(1) G2(0) G1(2) ...; consecutive blocks sit in consecutive slots.
-struct FoldRing {
-  int stages;
-  int wait_slot;         // slot of the next block to wait for
-  uint32_t wait_parity;
-  int run_slot;          // slot of the first block of the current group's tap run (also the next to release)
+// Streamed weights (S > 0): a ring with a COMPILE-TIME period.  Tap j of every conv sits in slot j mod S, so each
+// slot, each barrier and each barrier parity of the unrolled schedule is a constant of the code (the first version
+// carried a run-time cursor: ~45 dependent instructions per group of four MMAs, and the issuing thread, not the
+// tensor pipe, set the pace — profiles/r2_pair_epilogue_issue_bound.md).  Convs go through the ring in the order
+// G1(0) G1(1) G2(0) G1(2) G2(1) ...; slot s is used uses(s) times per conv, so use u of the c-th conv is phase
+// c * uses(s) + u of its barriers: parity = (uses(s) odd ? c & 1 : 0) ^ (u & 1) — one run-time bit.
+// A run of F = 2 consecutive taps (j, j + 1) must be contiguous for the stacked B operand: when j mod S = S - 1 the
+// tap j + 1 is ALSO loaded into a mirror slot S behind the ring (same barrier as slot 0, twice the bytes).
+template <int K, int S>
+struct FoldRingPlan {
+  static constexpr bool kMirror = S > 0 && K > S;
+  static constexpr int kSlots = S == 0 ? 2 * K : S + (kMirror ? 1 : 0);  // physical weight blocks in shared memory
+  static constexpr int kBars = S == 0 ? 2 * K : S;
+  __host__ __device__ static constexpr int uses(int s) { return (K - 1 - s) / (S > 0 ? S : 1) + 1; }
+  __host__ __device__ static constexpr uint32_t parity(int j, uint32_t cpar) {
+    return ((uses(j % (S > 0 ? S : 1)) & 1) ? cpar : 0u) ^ static_cast<uint32_t>((j / (S > 0 ? S : 1)) & 1);
+  }
 };
 
 // One conv of the pair, issued by a single thread.  Group oi (u = oi - CH) contracts the A operand
@@ -99,11 +109,14 @@ struct FoldRing {
 //   a_row0_16  (first row) * ROWB >> 4   — the slab row of shift 0
 //   a_shift16  (rows per block-group shift) * ROWB >> 4
 //   w_lo       resident: weight stage 0 of this conv; ring: stage 0 of the ring (smem address >> 4)
-template <int C, int K, bool RING>
+template <int C, int K, int S>
 __device__ __forceinline__ void fold_issue_conv(uint32_t acc, uint32_t a_base16, uint32_t a_phase16, int a_row0_16,
                                                 int a_shift16, uint32_t w_lo, uint32_t zero_lo, uint64_t* w_full,
-                                                uint64_t* w_empty, FoldRing& ring, bool wait_weights) {
+                                                uint64_t* w_empty, uint32_t cpar, bool wait_weights, int nosync = 0) {
   constexpr int F = 128 / C, CH = (K - 1) / 2, ROWB = C * 2, KSTEPS = C / 16, WB16 = (C * ROWB) >> 4;
+  constexpr bool RING = S > 0;
+  static_assert(!RING || F == 2, "the mirror slot covers runs of two taps");
+  using Plan = FoldRingPlan<K, S>;
   constexpr uint32_t SBO = 8 * ROWB;
   constexpr uint32_t LAYOUT = (C == 64) ? UMMA_LAYOUT_SW128 : (C == 32) ? UMMA_LAYOUT_SW64 : UMMA_LAYOUT_SW32;
   constexpr uint32_t desc_hi = ((SBO >> 4) & 0x3FFFu) | (1u << 14) | (LAYOUT << 29);
@@ -117,40 +130,29 @@ __device__ __forceinline__ void fold_issue_conv(uint32_t acc, uint32_t a_base16,
     const int b_blk = u + CH - h_hi, nblk = h_hi - h_lo + 1, d_col = (F - 1 - h_hi) * C;
     if (oi < K) {  // block oi is first used here
       if (RING) {
-        mbar_wait(&w_full[ring.wait_slot], ring.wait_parity);
-        if (++ring.wait_slot == ring.stages) { ring.wait_slot = 0; ring.wait_parity ^= 1; }
+        if (!(nosync & 1)) mbar_wait(&w_full[oi % (RING ? S : 1)], Plan::parity(oi, cpar));
         tc_fence_after();
       } else if (wait_weights) {
         mbar_wait(&w_full[oi], 0u);
         tc_fence_after();
       }
     }
-    const uint32_t b0 = RING ? w_lo + ring.run_slot * WB16 : w_lo + b_blk * WB16;
+    // the run's blocks are contiguous: resident at slot b_blk, streamed at slot b_blk mod S (mirror slot S behind S - 1)
+    const uint32_t b0 = w_lo + (RING ? b_blk % (RING ? S : 1) : b_blk) * WB16;
     if (oi == 0)  // D[128 x 128] = 0 * (first rows of weight block 0): one K = 16 MMA with the overwrite flag
       umma_bf16_lohi(acc, zero_lo, b0, desc_hi_alias, idesc0 | (static_cast<uint32_t>(128 >> 3) << 17), 0u);
     const uint32_t a_lo = a_base16 + hp * a_phase16 + static_cast<uint32_t>(a_row0_16 + s * a_shift16);
-    if (!RING || nblk == 1 || ring.run_slot + nblk <= ring.stages) {
-      const uint32_t idesc = idesc0 | (static_cast<uint32_t>((nblk * C) >> 3) << 17);
+    const uint32_t idesc = idesc0 | (static_cast<uint32_t>((nblk * C) >> 3) << 17);
 #pragma unroll
-      for (int ks = 0; ks < KSTEPS; ++ks) umma_bf16_lohi(acc + d_col, a_lo + ks * 2, b0 + ks * 2, desc_hi, idesc, 1u);
-    } else {  // the run wraps around the ring end: two groups, the second from slot 0
-      const int n1 = ring.stages - ring.run_slot;
-      const uint32_t idesc1 = idesc0 | (static_cast<uint32_t>((n1 * C) >> 3) << 17);
-      const uint32_t idesc2 = idesc0 | (static_cast<uint32_t>(((nblk - n1) * C) >> 3) << 17);
-#pragma unroll
-      for (int ks = 0; ks < KSTEPS; ++ks) umma_bf16_lohi(acc + d_col, a_lo + ks * 2, b0 + ks * 2, desc_hi, idesc1, 1u);
-#pragma unroll
-      for (int ks = 0; ks < KSTEPS; ++ks) umma_bf16_lohi(acc + d_col + n1 * C, a_lo + ks * 2, w_lo + ks * 2, desc_hi, idesc2, 1u);
-    }
-    if (RING && oi >= F - 1 && oi - F + 1 <= K - 1) {  // block oi - F + 1 (= the run's first) is done
-      umma_commit(&w_empty[ring.run_slot]);
-      if (++ring.run_slot == ring.stages) ring.run_slot = 0;
+    for (int ks = 0; ks < KSTEPS; ++ks) umma_bf16_lohi(acc + d_col, a_lo + ks * 2, b0 + ks * 2, desc_hi, idesc, 1u);
+    if (RING && oi >= F - 1 && oi - F + 1 <= K - 1) {  // block oi - F + 1 (= the run's first) has had its last use
+      if (!(nosync & 2)) umma_commit(&w_empty[(oi - F + 1) % (RING ? S : 1)]);
     }
   }
 }
 
-// RING = false: all 2K weight blocks stay in shared memory (slot conv*K + tap); RING = true: p.stages slots.
-template <int C, int K, bool RING>
+// S = 0: all 2K weight blocks stay in shared memory (slot conv*K + tap); S > 0: streamed through a ring of period S.
+template <int C, int K, int S>
 __global__ void __launch_bounds__(kFoldThreads, 1)
 conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_res,
                       const __grid_constant__ TcFoldParams p) {
@@ -158,7 +160,9 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
   constexpr int LOG2F = (F == 2) ? 1 : (F == 4) ? 2 : 3;
   constexpr int ROWB = C * 2;
   constexpr int WBLK = C * ROWB;  // one tap's [C rows][C] tile
-  const int STAGES = RING ? p.stages : 2 * K;
+  constexpr bool RING = S > 0;
+  using Plan = FoldRingPlan<K, S>;
+  constexpr int STAGES = Plan::kBars;  // weight barriers; Plan::kSlots blocks of shared memory
   constexpr uint32_t ACC_COLS = 128;
   constexpr uint32_t TMEM_COLS = 4 * ACC_COLS;
   static_assert(C == 64 || C == 32 || C == 16, "N = 128 = F x C");
@@ -172,8 +176,8 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
   uint8_t* slab = smem + kFoldZeroBytes;          // [2][slab_bytes]
   uint8_t* tbuf = slab + 2 * slab_bytes;          // [t_bufs][t_bytes]
   float* staging = reinterpret_cast<float*>(tbuf + p.t_bufs * t_bytes);  // [16][4 KB], 1024-aligned (TMA dst)
-  uint8_t* wst = reinterpret_cast<uint8_t*>(staging + kFoldEpiWarps * kFoldStageFloats);  // [STAGES][WBLK]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wst + STAGES * WBLK);
+  uint8_t* wst = reinterpret_cast<uint8_t*>(staging + kFoldEpiWarps * kFoldStageFloats);  // [Plan::kSlots][WBLK]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wst + Plan::kSlots * WBLK);
   uint64_t* slab_full = bars;        // [2]
   uint64_t* slab_empty = bars + 2;   // [2]
   uint64_t* slab_land = bars + 4;    // [2]  TMA landing barrier of a slab that needs its tail rows zeroed
@@ -236,18 +240,23 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
           }
         }
       } else {
-        int stage = 0; uint32_t phase = 0;
+        uint32_t cpar = 0;  // parity of the conv's position in the ring order
         auto load_conv = [&](const uint8_t* w) {
+#pragma unroll
           for (int j = 0; j < K; ++j) {
-            mbar_wait(&w_empty[stage], phase ^ 1);
+            constexpr int SS = RING ? S : 1;
+            const int slot = j % SS;
+            const bool mirror = Plan::kMirror && j >= SS && slot == 0;  // tap j also closes the run (j - 1, j) behind slot S - 1
+            mbar_wait(&w_empty[slot], Plan::parity(j, cpar) ^ 1);
             if (FOLD_DBG(64)) {
-              mbar_arrive(&w_full[stage]);
+              mbar_arrive(&w_full[slot]);
             } else {
-              mbar_arrive_expect_tx(&w_full[stage], WBLK);
-              bulk_load_1d(wst + stage * WBLK, w + static_cast<size_t>(j) * WBLK, WBLK, &w_full[stage]);
+              mbar_arrive_expect_tx(&w_full[slot], mirror ? 2 * WBLK : WBLK);
+              bulk_load_1d(wst + slot * WBLK, w + static_cast<size_t>(j) * WBLK, WBLK, &w_full[slot]);
+              if (mirror) bulk_load_1d(wst + SS * WBLK, w + static_cast<size_t>(j) * WBLK, WBLK, &w_full[slot]);
             }
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
+          cpar ^= 1;
         };
         load_conv(p.w1);                       // G1(0)
         for (int i = 0; i < n_my; ++i) {
@@ -314,7 +323,7 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
       const uint32_t slab_phase16 = static_cast<uint32_t>(p.slab_phase_bytes) >> 4, xt_phase16 = static_cast<uint32_t>(p.xt_phase_bytes) >> 4;
       const int a1_row0_16 = p.a1_row0 * (ROWB >> 4), a2_row0_16 = p.a2_row0 * (ROWB >> 4);
       const int a1_shift16 = p.d1 * (ROWB >> 4), a2_shift16 = ROWB >> 4;
-      FoldRing ring{STAGES, 0, 0u, 0};
+      uint32_t cpar = 0;  // streamed weights: parity of the conv's position in the ring order G1(0) G1(1) G2(0) G1(2) ...
       bool w_seen1 = false, w_seen2 = false;  // resident weights: waited for during the first conv 1 / conv 2 only
       auto g1 = [&](int i) {
         const int buf = i & 1;
@@ -323,8 +332,9 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
         mbar_wait(&slab_full[buf], ph);
         tc_fence_after();
         if (!FOLD_DBG(1))
-          fold_issue_conv<C, K, RING>(tmem_base + buf * ACC_COLS, slab_lo + buf * slab_buf16, slab_phase16, a1_row0_16, a1_shift16,
-                                    wst_lo, zero_lo, w_full, w_empty, ring, !w_seen1);
+          fold_issue_conv<C, K, S>(tmem_base + buf * ACC_COLS, slab_lo + buf * slab_buf16, slab_phase16, a1_row0_16, a1_shift16,
+                                   wst_lo, zero_lo, w_full, w_empty, cpar, !w_seen1);
+        cpar ^= 1;
         umma_commit(&slab_empty[buf]);
         umma_commit(&d1_full[buf]);
         w_seen1 = true;
@@ -338,9 +348,10 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
         mbar_wait(&d2_empty[buf], ph ^ 1);
         tc_fence_after();
         if (!FOLD_DBG(1))
-          fold_issue_conv<C, K, RING>(tmem_base + (2 + buf) * ACC_COLS, t_lo + tbi * t_buf16, xt_phase16, a2_row0_16, a2_shift16,
-                                    RING ? wst_lo : wst_lo + K * (WBLK >> 4), zero_lo, RING ? w_full : w_full + K,
-                                    RING ? w_empty : w_empty + K, ring, !w_seen2);
+          fold_issue_conv<C, K, S>(tmem_base + (2 + buf) * ACC_COLS, t_lo + tbi * t_buf16, xt_phase16, a2_row0_16, a2_shift16,
+                                   RING ? wst_lo : wst_lo + K * (WBLK >> 4), zero_lo, RING ? w_full : w_full + K,
+                                   RING ? w_empty : w_empty + K, cpar, !w_seen2);
+        cpar ^= 1;
         umma_commit(&t_empty[tbi]);
         umma_commit(&d2_full[buf]);
         w_seen2 = true;
@@ -527,19 +538,28 @@ size_t conv_fold_smem_bytes(int c, int slab_phase_bytes, int xt_phase_bytes, int
          static_cast<size_t>(stages) * c * c * 2 + (34 + 2 * stages) * 8 + 16;
 }
 
-// (C, k, streamed?) combinations the kernel is instantiated for: C = 16 / 32 keep their weights resident for
-// every k; C = 64 does for k = 3 and streams from k = 5 on.  (C = 32, k = 3 is left to conv_pair_tc.cu.)
-bool conv_fold_has_kernel(int c, int k, bool ring) {
-  if (c == 16) return !ring && (k == 3 || k == 5 || k == 7 || k == 9 || k == 11);
-  if (c == 32) return !ring && (k == 5 || k == 7 || k == 9 || k == 11);
-  if (c == 64) return ring ? (k == 5 || k == 7 || k == 9 || k == 11) : k == 3;
+// (C, k, ring period) combinations the kernel is instantiated for; period 0 = resident weights.  C = 16 / 32 keep
+// their weights resident for every k; C = 64 does for k = 3 and streams from k = 5 on, through a ring of period k (no
+// mirror slot), 6, 5 or 4 (+ mirror) — whichever fits next to the slabs (api.cu::fold_geometry).  (C = 32, k = 3 is left
+// to conv_pair_tc.cu.)
+bool conv_fold_has_kernel(int c, int k, int s) {
+  if (c == 16) return s == 0 && (k == 3 || k == 5 || k == 7 || k == 9 || k == 11);
+  if (c == 32) return s == 0 && (k == 5 || k == 7 || k == 9 || k == 11);
+  if (c == 64) {
+    if (k == 3) return s == 0;
+    if (k == 5) return s == 5;
+    if (k == 7) return s == 7 || s == 5 || s == 4;
+    if (k == 9 || k == 11) return s == 6 || s == 5 || s == 4;
+  }
   return false;
 }
+// physical weight blocks of shared memory the (k, period) kernel uses
+int conv_fold_weight_slots(int k, int s) { return s == 0 ? 2 * k : s + (k > s ? 1 : 0); }
 
-template <int C, int K, bool RING>
+template <int C, int K, int S>
 static cudaError_t launch_fold(const CUtensorMap& m, const CUtensorMap& mr, const TcFoldParams& p, size_t smem, int grid,
                                cudaStream_t st) {
-  auto kern = conv_pair_fold_kernel<C, K, RING>;
+  auto kern = conv_pair_fold_kernel<C, K, S>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
@@ -555,16 +575,19 @@ static cudaError_t launch_fold(const CUtensorMap& m, const CUtensorMap& mr, cons
   return cudaLaunchKernelEx(&cfg, kern, m, mr, p);
 }
 
-// mr: fp32 tile map over the folded residual view [B][L/F][128]
-cudaError_t launch_conv_pair_fold(int c, int k, bool ring, const CUtensorMap& m, const CUtensorMap& mr, const TcFoldParams& p,
+// mr: fp32 tile map over the folded residual view [B][L/F][128]; s: ring period (0 = resident weights)
+cudaError_t launch_conv_pair_fold(int c, int k, int s, const CUtensorMap& m, const CUtensorMap& mr, const TcFoldParams& p,
                                   size_t smem, int grid, cudaStream_t st) {
-  if (!conv_fold_has_kernel(c, k, ring)) return cudaErrorInvalidValue;
-#define HG_FOLD_CASE(CV, KV, RV) \
-  if (c == CV && k == KV && ring == RV) return launch_fold<CV, KV, RV>(m, mr, p, smem, grid, st);
-  HG_FOLD_CASE(16, 3, false) HG_FOLD_CASE(16, 5, false) HG_FOLD_CASE(16, 7, false) HG_FOLD_CASE(16, 9, false) HG_FOLD_CASE(16, 11, false)
-  HG_FOLD_CASE(32, 5, false) HG_FOLD_CASE(32, 7, false) HG_FOLD_CASE(32, 9, false) HG_FOLD_CASE(32, 11, false)
-  HG_FOLD_CASE(64, 3, false)
-  HG_FOLD_CASE(64, 5, true) HG_FOLD_CASE(64, 7, true) HG_FOLD_CASE(64, 9, true) HG_FOLD_CASE(64, 11, true)
+  if (!conv_fold_has_kernel(c, k, s)) return cudaErrorInvalidValue;
+#define HG_FOLD_CASE(CV, KV, SV) \
+  if (c == CV && k == KV && s == SV) return launch_fold<CV, KV, SV>(m, mr, p, smem, grid, st);
+  HG_FOLD_CASE(16, 3, 0) HG_FOLD_CASE(16, 5, 0) HG_FOLD_CASE(16, 7, 0) HG_FOLD_CASE(16, 9, 0) HG_FOLD_CASE(16, 11, 0)
+  HG_FOLD_CASE(32, 5, 0) HG_FOLD_CASE(32, 7, 0) HG_FOLD_CASE(32, 9, 0) HG_FOLD_CASE(32, 11, 0)
+  HG_FOLD_CASE(64, 3, 0)
+  HG_FOLD_CASE(64, 5, 5)
+  HG_FOLD_CASE(64, 7, 7) HG_FOLD_CASE(64, 7, 5) HG_FOLD_CASE(64, 7, 4)
+  HG_FOLD_CASE(64, 9, 6) HG_FOLD_CASE(64, 9, 5) HG_FOLD_CASE(64, 9, 4)
+  HG_FOLD_CASE(64, 11, 6) HG_FOLD_CASE(64, 11, 5) HG_FOLD_CASE(64, 11, 4)
 #undef HG_FOLD_CASE
   return cudaErrorInvalidValue;
 }
