@@ -24,6 +24,11 @@ from oracle import fixtures as fx  # noqa: E402
 from _util import make_generator  # noqa: E402
 
 VARIANTS = [("N=C", {"HG_FOLD": "0"}), ("fold", {"HG_FOLD": "2"}), ("default", {})]
+if os.environ.get("VARIANTS"):  # e.g. VARIANTS="forward:HG_TILE_ORDER=0;alternate:" — any plan-creation switches
+    VARIANTS = []
+    for item in os.environ["VARIANTS"].split(";"):
+        name, _, kv = item.partition(":")
+        VARIANTS.append((name, dict(x.split("=") for x in kv.split(",") if x)))
 ROUNDS = int(os.environ.get("ROUNDS", "6"))
 
 
@@ -69,7 +74,7 @@ def main():
     for n in models:
         print(f"{n} | {mean(step[n]):.3f} | {min(step[n]):.3f} | {sum(mean(v) for v in pairs[n].values()):.3f} | {digests[n]}")
     print("launch | " + " | ".join(models))
-    for ln in sorted(pairs["N=C"]):
+    for ln in sorted(pairs[VARIANTS[0][0]]):
         print(ln, "|", " | ".join(f"{mean(pairs[n][ln]):.4f}" for n in models))
     assert len(set(digests.values())) == 1, digests
 

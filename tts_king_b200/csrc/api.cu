@@ -71,6 +71,15 @@ static int fail(int code, const char* fmt, ...) {
 // Every entry point that touches a device runs with that device current and puts the caller's device
 // back on return: a process that drives several GPUs from one thread (or whose garbage collector destroys
 // a plan at an arbitrary point) must not find its current device changed behind its back.
+// see common.cuh::ragged_finish — consecutive launches of a forward walk their tiles in opposite directions
+namespace hg {
+thread_local int hg_reverse_tiles = -1;
+}
+struct TileOrderScope {
+  explicit TileOrderScope(bool alternate) { hg_reverse_tiles = alternate ? 0 : -1; }
+  ~TileOrderScope() { hg_reverse_tiles = -1; }
+};
+
 struct DeviceScope {
   int prev = -1;
   bool changed = false;
@@ -303,6 +312,7 @@ static void init_plan_env(HgPlan* p, int device) {
   p->ctas_per_sm = env_int("HG_TC_CTAS_PER_SM", 1);
   p->fuse_pairs = env_int("HG_FUSE_PAIRS", 1) != 0;
   p->fold_pairs = env_int("HG_FOLD", 1) != 0;
+  p->tile_alternate = env_int("HG_TILE_ORDER", 1) != 0;
   p->fold_force = env_int("HG_FOLD", 1) == 2;
   // Off by default: measured on B200 (16 x 800 frames) the fused ResBlock is SLOWER than its three fused pairs
   // (0.96 vs 0.73 ms at C = 64, 0.88 vs 0.71 ms at C = 32; profiles/r2_resblock_fusion_experiment.md) — the twelve
@@ -1375,6 +1385,7 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
   if (workspace_bytes < ws.bytes)
     return fail(HG_ENOMEM, "workspace too small: %zu < %zu bytes", workspace_bytes, ws.bytes);
   DEVICE_SCOPE(plan->device);
+  TileOrderScope tile_order(plan->tile_alternate);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const HgConfig& c = plan->cfg;
   const std::vector<Layer>& LY = active_layers(plan, precision);
@@ -1702,6 +1713,7 @@ extern "C" int hg_stack_forward(HgPlan* plan, const float* x, int64_t sB, int64_
   layout_stack(plan, B, T, precision, workspace, &ws);
   if (workspace_bytes < ws.bytes) return fail(HG_ENOMEM, "workspace too small: %zu < %zu bytes", workspace_bytes, ws.bytes);
   DEVICE_SCOPE(plan->device);
+  TileOrderScope tile_order(plan->tile_alternate);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int fmt = a_fmt_of(precision);
   const int n = static_cast<int>(plan->layers.size());

@@ -24,10 +24,12 @@ constexpr int kMaxTaps = 16;
 constexpr int kMaxRaggedItems = 64;
 struct RaggedPrefix {
   int n;
+  int rev_total;  // > 0: the launch walks its tiles backwards (tile index t -> rev_total - 1 - t), see hg_reverse_tiles
   int prefix[kMaxRaggedItems + 1];
 };
 #ifdef __CUDACC__
 __device__ __forceinline__ void decode_tile(const RaggedPrefix& r, int tiles_per_item, int t, int& b, int& tile) {
+  if (r.rev_total) t = r.rev_total - 1 - t;
   if (r.n == 0) {
     b = t / tiles_per_item;
     tile = t - b * tiles_per_item;
@@ -47,10 +49,21 @@ struct RaggedItems {
   int n;
   int valid_rows[kMaxRaggedItems];
 };
+// Tile order: consecutive launches of a forward walk their tiles in OPPOSITE directions.  Each layer streams
+// hundreds of MB through the 126 MB L2; what is left there when a launch ends is the END of the tensors it wrote,
+// which a forward-walking consumer would only reach after having evicted it.  Walking backwards, the next launch
+// starts on those lines (profiles/r2_tile_order_l2.md).  The flag flips with every table built (= every launch) and
+// is reset at the start of a forward, so the order is a pure function of the layer sequence.
+extern thread_local int hg_reverse_tiles;  // api.cu; -1 = alternation switched off (HG_TILE_ORDER=0)
+inline int ragged_finish(RaggedPrefix* r, int total) {
+  r->rev_total = hg_reverse_tiles > 0 ? total : 0;
+  if (hg_reverse_tiles >= 0) hg_reverse_tiles ^= 1;
+  return total;
+}
 inline int ragged_fill(RaggedPrefix* r, const RaggedItems* items, int B, int rows, int tile_rows) {
   const int dense = (rows + tile_rows - 1) / tile_rows;
   r->n = 0;
-  if (!items || items->n == 0) return B * dense;
+  if (!items || items->n == 0) return ragged_finish(r, B * dense);
   r->n = B;
   r->prefix[0] = 0;
   for (int b = 0; b < B; ++b) {
@@ -58,7 +71,7 @@ inline int ragged_fill(RaggedPrefix* r, const RaggedItems* items, int B, int row
     if (v < 1) v = 1;
     r->prefix[b + 1] = r->prefix[b] + (v + tile_rows - 1) / tile_rows;
   }
-  return r->prefix[B];
+  return ragged_finish(r, r->prefix[B]);
 }
 
 enum OperandFmt : int { A_BF16 = 0, A_BF16_SPLIT = 1, A_F32 = 2 };

@@ -119,6 +119,7 @@ struct HgPlan {
   bool fuse_pairs = true;  // HG_FUSE_PAIRS=0: never use the fused ResBlock-pair kernel
   bool fold_pairs = true;  // HG_FOLD=0: fused pairs run on conv_pair_tc.cu (N = C) instead of conv_pair_fold.cu (N = 128)
   bool fuse_blocks = false;  // HG_CHAIN=1: fuse a whole k = 3 ResBlock1 into one launch (conv_chain_tc.cu; slower than its pairs, see api.cu)
+  bool tile_alternate = true;  // consecutive launches walk their tiles in opposite directions (HG_TILE_ORDER=0: all forward)
   bool fold_force = false;  // HG_FOLD=2: ... and on conv_pair_fold.cu wherever it applies, not only where it is faster
   bool epi_tma = true;     // HG_EPI_TMA=0: always use the generic (LSU) epilogue in conv_tc
   bool use_tc2 = true;     // HG_TC2=0: never use the CTA-pair (cta_group::2) kernel for the 256/128-channel convs
