@@ -115,3 +115,40 @@ void og_to_int16(const float* wav, int64_t n, float max_wav_value, int16_t* out)
     out[i] = (int16_t)(uint16_t)(uint32_t)t;
   }
 }
+
+/* The fused-pair epilogue's x / num_kernels for num_kernels = 3 (hifi/models.py:196), as
+ * tts_king_b200/csrc/common.cuh::div3_rn computes it: q0 = x * RN(1/3), rem = fma(-3, q0, x),
+ * q = fma(rem, RN(1/3), q0), sign of x copied onto q; infinities and NaNs take the ordinary division.
+ * og_div3_sweep walks the bit patterns start, start + stride, ... (count of them) and returns how many
+ * differ from the IEEE quotient x / 3.0f (NaN counts as equal to NaN); *first_bad receives the first one. */
+static float og_div3(float v) {
+  const float r = 0x1.555556p-2f;
+  if (!(fabsf(v) < INFINITY)) return v / 3.0f;
+  float q0 = v * r;
+  float rem = fmaf(-3.0f, q0, v);
+  float q = fmaf(rem, r, q0);
+  uint32_t qb, vb;
+  memcpy(&qb, &q, 4);
+  memcpy(&vb, &v, 4);
+  qb = (qb & 0x7fffffffu) | (vb & 0x80000000u);
+  memcpy(&q, &qb, 4);
+  return q;
+}
+int64_t og_div3_sweep(uint32_t start, uint32_t stride, int64_t count, uint32_t* first_bad) {
+  int64_t bad = 0;
+  uint32_t b = start;
+  for (int64_t i = 0; i < count; ++i, b += stride) {
+    float v, ref, got;
+    uint32_t rb, gb;
+    memcpy(&v, &b, 4);
+    ref = v / 3.0f;
+    got = og_div3(v);
+    memcpy(&rb, &ref, 4);
+    memcpy(&gb, &got, 4);
+    if (rb != gb && !(ref != ref && got != got)) {
+      if (bad == 0 && first_bad) *first_bad = b;
+      ++bad;
+    }
+  }
+  return bad;
+}

@@ -286,6 +286,35 @@ __device__ __forceinline__ uint2 lrelu_pack4(float4 v, float slope) {
   return pack_bf16x4(fmaxf(v.x, lo.x), fmaxf(v.y, lo.y), fmaxf(v.z, hi.x), fmaxf(v.w, hi.y));
 }
 
+// x / 3 in three packed instructions instead of __fdiv_rn's ~10 per element (hifi/models.py:196 divides the MRF sum
+// by num_kernels = 3): q0 = x * RN(1/3); rem = fma(-3, q0, x) (exact); q = fma(rem, RN(1/3), q0) is the correctly
+// rounded quotient (Markstein); the sign is copied from x so that -0 stays -0.  Checked against x / 3.0f for ALL
+// 2^32 bit patterns (tests/test_oracle.py::test_div3_sequence_matches_ieee_division runs the C restatement over a
+// sample plus the edge cases): the only differences are +-inf (rem = inf - inf), which take the __fdiv_rn path.
+__device__ __forceinline__ float2 fma_f32x2(float2 a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float copy_sign_bit(float mag, float sgn) {
+  return __uint_as_float((__float_as_uint(mag) & 0x7fffffffu) | (__float_as_uint(sgn) & 0x80000000u));
+}
+__device__ __forceinline__ float4 div3_rn(float4 v) {
+  const float big = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+  if (!(big < __int_as_float(0x7f800000)))  // an infinity or a NaN among the four
+    return make_float4(__fdiv_rn(v.x, 3.f), __fdiv_rn(v.y, 3.f), __fdiv_rn(v.z, 3.f), __fdiv_rn(v.w, 3.f));
+  const float2 r = make_float2(0x1.555556p-2f, 0x1.555556p-2f), m3 = make_float2(-3.f, -3.f);
+  const float2 lo = make_float2(v.x, v.y), hi = make_float2(v.z, v.w);
+  const float2 ql = mul_f32x2(lo, r), qh = mul_f32x2(hi, r);
+  const float2 l2 = fma_f32x2(fma_f32x2(m3, ql, lo), r, ql), h2 = fma_f32x2(fma_f32x2(m3, qh, hi), r, qh);
+  return make_float4(copy_sign_bit(l2.x, v.x), copy_sign_bit(l2.y, v.y), copy_sign_bit(h2.x, v.z), copy_sign_bit(h2.y, v.w));
+}
+
 // The tail of a fused pair's E2 (conv_pair_tc.cu, conv_pair_fold.cu), written for INSTRUCTION COUNT — those kernels'
 // epilogue warps are issue-bound (profiles/r2_pair_epilogue_issue_bound.md).  The thread holds eight float4: rows
 // 0, 4, ..., 28 of its warp item at four consecutive columns, residual already added.  `off` is the element offset of
@@ -305,7 +334,10 @@ __device__ __forceinline__ void epilogue_tail8(const EpiParams& e, long long off
 #pragma unroll
     for (int ii = 0; ii < 8; ++ii) v[ii] = add4(a[ii], v[ii]);
   }
-  if (e.post_div > 0.f) {
+  if (e.post_div == 3.f) {  // V1's three resblock kernels
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) v[ii] = div3_rn(v[ii]);
+  } else if (e.post_div > 0.f) {
     const float d = e.post_div;
 #pragma unroll
     for (int ii = 0; ii < 8; ++ii) {
