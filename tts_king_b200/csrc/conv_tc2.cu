@@ -336,7 +336,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             else if (work + npairs < p.total_work) prefetch_res(work + npairs, sub);
           }
         }
-        if (p.epi.post_div > 0.f) {  // x = xs / num_kernels   (:196)
+        if (p.epi.post_div == 3.f) {  // x = xs / num_kernels   (:196), V1's three kernels: common.cuh::div3_rn
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 t = div3_rn(make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+          }
+        } else if (p.epi.post_div > 0.f) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __fdiv_rn(v[i], p.epi.post_div);
         }
