@@ -1094,15 +1094,15 @@ static bool fold_geometry(int c, int k, int d1, int L, FoldTiling* t) {
 }
 
 // Where the time-folded kernel is the faster of the two pair kernels (interleaved A/B on B200, 16 x 800 frames,
-// tools/pair_modes.py, profiles/r2_v10_pair_kernel_ab.txt): it wins where the N = C kernel is bound by MMA operand
-// fetch — 32 channels from k = 5 up (0.43 -> 0.28 ms at k = 11) and 64 channels from k = 7 up (0.34 -> 0.31 ms at
-// k = 7, 0.52 -> 0.38-0.44 ms at k = 11) — and loses a few percent where the pair is HBM-bound (k = 3), and at
-// 64 channels, k >= 9 on the last pair of a stage (MRF sum read in the epilogue, and its dilation-5 slab leaves
-// the shallowest weight ring: 0.54 vs 0.52 ms).  HG_FOLD=2 forces it wherever it applies (tests, A/B).
+// tools/pair_modes.py, profiles/r2_v11_pair_kernel_ab.txt): it wins where the N = C kernel is bound by MMA operand
+// fetch — 32 channels from k = 5 up (0.43 -> 0.27 ms at k = 11) and 64 channels from k = 7 up (0.34 -> 0.31-0.34 ms
+// at k = 7, 0.51 -> 0.39-0.51 ms at k = 11) — and loses a few percent where the pair is HBM-bound (k = 3).
+// HG_FOLD=2 forces it wherever it applies (tests, A/B).
 static bool fold_pays(const HgPlan* plan, const Layer& l2, bool mrf_accumulate) {
+  (void)mrf_accumulate;
   if (plan->fold_force || l2.cin == 16) return true;  // 16 channels: the alternative is the CUDA-core kernel
   if (l2.cin == 32) return l2.k >= 5;
-  return l2.k >= 7 && !(mrf_accumulate && l2.k >= 9);
+  return l2.k >= 7;
 }
 
 static bool fold_fusable(const HgPlan* plan, const Layer& l1, const Layer& l2, int precision, int L, FoldTiling* t) {

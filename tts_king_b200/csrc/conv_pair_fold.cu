@@ -191,6 +191,7 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
   uint64_t* w_full = bars + 34;      // [STAGES]
   uint64_t* w_empty = w_full + STAGES;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_empty + STAGES);
+  float* bias1_s = reinterpret_cast<float*>(tmem_ptr_smem + 4);  // [C] conv 1 bias: E1 reads it with broadcast LDS
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_my = p.total_work > static_cast<int>(blockIdx.x)
@@ -202,6 +203,9 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
     *reinterpret_cast<uint4*>(zero_a + lane * 32) = make_uint4(0u, 0u, 0u, 0u);
     *reinterpret_cast<uint4*>(zero_a + lane * 32 + 16) = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async();
+    // a weight, not a product of the previous launch: may be read before griddepcontrol.wait.  (From global memory
+    // the same-address float4 loads of E1 cost four L1 wavefronts each — 512 per tile on a saturated data pipe.)
+    if (lane < C / 4) reinterpret_cast<float4*>(bias1_s)[lane] = __ldg(reinterpret_cast<const float4*>(p.bias1) + lane);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -397,6 +401,7 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
     const int n2 = c02m + c4 * 4;
     const int tau0 = p.fdiv * blk1 + r1;  // xt row of (this M row, phase 0), tile-relative; phase h adds h * d1
     const float slope1 = p.slope;
+    const uint32_t bias1_a = smem_u32(bias1_s);
 
     // E1: D1 -> (+b1, leaky_relu, bf16) -> xt phase slabs in UMMA layout; two 16-column items per warp
     auto e1 = [&](int i, const TileAt& at) {
@@ -416,8 +421,8 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
         const int q = (16 * j) / C, c0 = (16 * j) % C;
         const int tau = tau0 + (F - 1 - q) * p.d1;
         const bool inside = static_cast<unsigned>(at.g0 + tau) < static_cast<unsigned>(p.L);
-        const float4* bp = reinterpret_cast<const float4*>(p.bias1 + c0);
-        const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1), b2 = __ldg(bp + 2), b3 = __ldg(bp + 3);
+        const uint32_t bp = bias1_a + c0 * 4;
+        const float4 b0 = lds128(bp), b1 = lds128(bp + 16), b2 = lds128(bp + 32), b3 = lds128(bp + 48);
         tmem_ld_wait();
         if (j + 4 >= 8) {
           tc_fence_before();
@@ -535,7 +540,7 @@ size_t conv_fold_smem_bytes(int c, int slab_phase_bytes, int xt_phase_bytes, int
   const int f = 128 / c;
   return 1024 + kFoldZeroBytes + 2 * static_cast<size_t>(f) * slab_phase_bytes +
          static_cast<size_t>(t_bufs) * f * xt_phase_bytes + kFoldEpiWarps * kFoldStageFloats * 4 +
-         static_cast<size_t>(stages) * c * c * 2 + (34 + 2 * stages) * 8 + 16;
+         static_cast<size_t>(stages) * c * c * 2 + (34 + 2 * stages) * 8 + 16 + 256;
 }
 
 // (C, k, ring period) combinations the kernel is instantiated for; period 0 = resident weights.  C = 16 / 32 keep

@@ -72,6 +72,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
   uint64_t* w_full = bars + 32;      // [stages]
   uint64_t* w_empty = w_full + p.stages;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_empty + p.stages);
+  float* bias1_s = reinterpret_cast<float*>(tmem_ptr_smem + 4);  // [C] conv 1 bias: E1 reads it with broadcast LDS
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h2 = (p.k - 1) >> 1;
@@ -82,6 +83,9 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
                        : 0;
 
   if (warp == 0 && lane == 0) { prefetch_tensormap(&map_in); prefetch_tensormap(&map_res); }
+  // conv 1's bias is a weight, not a product of the previous launch: it may be read before griddepcontrol.wait.  (From
+  // global memory the same-address float4 loads of E1 cost four L1 wavefronts each on a saturated data pipe.)
+  if (warp == 2 && lane < C / 4) reinterpret_cast<float4*>(bias1_s)[lane] = __ldg(reinterpret_cast<const float4*>(p.bias1) + lane);
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < 2; ++i) {
@@ -251,6 +255,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
     const uint32_t tb_s = smem_u32(tbuf);
     const uint32_t stg_s = smem_u32(stg);
     const float slope1 = p.slope;
+    const uint32_t bias1_a = smem_u32(bias1_s);
 
     // E1: D1 -> (+b1, leaky_relu, bf16) -> xt tile in UMMA layout; two (sub-tile, 16-column) items
     auto e1 = [&](int i, const TileAt& at) {
@@ -272,8 +277,8 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
         tmem_ld_32x16(tmem_acc + ms * N_T + c0, r);
         const int row = ms * 128 + quarter * 32 + lane;  // row of the xt tile; global time index m0 - h2 + row
         const bool inside = static_cast<unsigned>(at.m0 - h2 + row) < static_cast<unsigned>(p.L);
-        const float4* bp = reinterpret_cast<const float4*>(p.bias1 + c0);
-        const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1), b2 = __ldg(bp + 2), b3 = __ldg(bp + 3);
+        const uint32_t bp = bias1_a + c0 * 4;
+        const float4 b0 = lds128(bp), b1 = lds128(bp + 16), b2 = lds128(bp + 32), b3 = lds128(bp + 48);
         tmem_ld_wait();
         if (j + 4 >= ITEMS) {
           tc_fence_before();
@@ -386,7 +391,7 @@ conv_pair_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
 size_t conv_pair_smem_bytes(int c, int slab_rows, int t_rows, int t_bufs, int stages) {
   const int rowb = c * 2;
   return 1024 + 2 * static_cast<size_t>(slab_rows) * rowb + static_cast<size_t>(t_bufs) * t_rows * rowb +
-         static_cast<size_t>(stages) * c * rowb + kPairEpiWarps * kPairStageFloats * 4 + (32 + 2 * stages) * 8 + 16;
+         static_cast<size_t>(stages) * c * rowb + kPairEpiWarps * kPairStageFloats * 4 + (32 + 2 * stages) * 8 + 16 + 256;
 }
 
 template <int C, int MS, bool DBG>
