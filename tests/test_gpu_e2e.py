@@ -397,6 +397,53 @@ def test_alternative_kernel_paths_keep_parity(env):
     assert res["bf16"][1] >= BF16_SNR_DB, res
 
 
+def test_concurrent_resblocks_are_bit_identical_to_the_serial_schedule():
+    """Short inputs run the ResBlocks of a stage on separate streams (api.cu::concurrent_stage): same kernels, same
+    MRF summation order, so the waveform must be the serial schedule's bit for bit — eager, ragged, int16, as a CUDA
+    graph, and with only some of the stages under the size threshold.  The switch is read at plan creation, so the
+    two schedules are two generators in one subprocess."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import os, sys, json, torch\n"
+        f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})\n"
+        "from oracle import fixtures as fx\n"
+        "from _util import make_generator\n"
+        "res = {}\n"
+        "for name, cfg in (('v1', fx.V1), ('v3_rb2', fx.V3_RB2), ('v2_narrow', fx.V2_NARROW)):\n"
+        "    for prec in ('bf16', 'fp32'):\n"
+        "        gens = {}\n"
+        "        for tag, kelems in (('serial', '0'), ('conc', '2560'), ('stage0', '600')):\n"
+        "            os.environ['HG_CONCURRENT_KELEMS'] = kelems\n"
+        "            gens[tag] = make_generator(cfg, precision=prec).cuda()\n"
+        "        ok = True\n"
+        "        with torch.no_grad():\n"
+        "            for B, T in ((1, 64), (1, 256), (3, 37), (2, 300)):\n"
+        "                mel = fx.synthetic_mel(B, T, seed=7).cuda()\n"
+        "                ref = gens['serial'](mel)\n"
+        "                for tag in ('conc', 'stage0'):\n"
+        "                    ok &= bool(torch.equal(gens[tag](mel), ref))\n"
+        "                    ok &= bool(torch.equal(gens[tag](mel), ref))  # again: buffers and events are reused\n"
+        "                ok &= bool(torch.equal(gens['conc'].generate_int16(mel), gens['serial'].generate_int16(mel)))\n"
+        "                if B > 1:\n"
+        "                    fr = [T, max(1, T // 3), T - 1][:B]\n"
+        "                    ok &= bool(torch.equal(gens['conc'].forward_ragged(mel, fr), gens['serial'].forward_ragged(mel, fr)))\n"
+        "            mel = fx.synthetic_mel(1, 128, seed=9).cuda()\n"
+        "            run = gens['conc'].make_graphed(1, 128)\n"
+        "            ok &= bool(torch.equal(run(mel), gens['serial'](mel)))\n"
+        "            ok &= bool(torch.equal(run(mel), gens['serial'](mel)))\n"
+        "        res[name + '/' + prec] = ok\n"
+        "print(json.dumps(res))\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert all(res.values()), res
+
+
 @pytest.mark.parametrize("rates,kernels", [((5, 2), (10, 4)), ((2, 2), (8, 4)), ((8, 2), (15, 4))])
 def test_unsupported_upsampler_shapes_fail_loudly(rates, kernels):
     """hg_plan_create rejects ConvTranspose1d shapes whose output is not exactly rate x input (odd k - u,

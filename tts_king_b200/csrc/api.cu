@@ -313,6 +313,7 @@ static void init_plan_env(HgPlan* p, int device) {
   p->fuse_pairs = env_int("HG_FUSE_PAIRS", 1) != 0;
   p->fold_pairs = env_int("HG_FOLD", 1) != 0;
   p->tile_alternate = env_int("HG_TILE_ORDER", 1) != 0;
+  p->concurrent_elems = static_cast<long long>(env_int("HG_CONCURRENT_KELEMS", 2560)) * 1024;
   p->fold_force = env_int("HG_FOLD", 1) == 2;
   // Off by default: measured on B200 (16 x 800 frames) the fused ResBlock is SLOWER than its three fused pairs
   // (0.96 vs 0.73 ms at C = 64, 0.88 vs 0.71 ms at C = 32; profiles/r2_resblock_fusion_experiment.md) — the twelve
@@ -598,6 +599,9 @@ extern "C" int hg_plan_destroy(HgPlan* plan) {
   for (auto& l : plan->layers) free_layer(l);
   for (auto& l : plan->layers_pad) free_layer(l);
   for (auto& l : plan->layers_small) if (l.loaded) free_layer(l);
+  for (cudaStream_t sst : plan->side_stream) if (sst) cudaStreamDestroy(sst);
+  for (cudaEvent_t ev : plan->ev_done) if (ev) cudaEventDestroy(ev);
+  if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
   delete plan;
   return HG_OK;
 }
@@ -1279,8 +1283,32 @@ struct Workspace {
   float* F[3];
   OperandBuf A[3];
   OperandBuf mel;
+  // short inputs only (concurrent_eligible): private x / operand buffers of ResBlocks 1..K-1 of a stage
+  float* FB[kMaxSideStreams];
+  OperandBuf AB[kMaxSideStreams][2];
   size_t bytes;
 };
+
+// Short inputs leave most of the GPU idle in every launch (one 256-frame utterance: 8 .. 132 tiles for 148 SMs) and
+// the forward is a chain of ~11 us launches.  The K ResBlocks of a stage only meet in the MRF sum, so they run on
+// separate streams there: the chain is one block long instead of K.  Decided per stage on its activation size
+// (items x rows x channels; a stage of one 256-frame V1 utterance has 0.5 / 2.1 / 2.1 / 2.1 M elements): launches
+// that fill the GPU by themselves only get in each other's way (tools/concurrent_blocks_ab.py).
+static bool concurrent_stage(const HgPlan* plan, long long elems) {
+  return plan->concurrent_elems > 0 && plan->cfg.num_kernels > 1 && plan->cfg.num_kernels - 1 <= kMaxSideStreams &&
+         elems <= plan->concurrent_elems;
+}
+// whether any stage of this forward may run that way (then the workspace holds the blocks' private buffers)
+static bool concurrent_eligible(const HgPlan* plan, int B, int T, int precision) {
+  const std::vector<Layer>& LY = active_layers(plan, precision);
+  long long L = T;
+  for (int i = 0; i < plan->cfg.num_upsamples; ++i) {
+    const Layer& up = LY[1 + i];
+    L = (L - 1) * up.stride - 2 * up.pad + up.k;
+    if (L >= 1 && concurrent_stage(plan, static_cast<long long>(B) * L * up.cout)) return true;
+  }
+  return false;
+}
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -1317,6 +1345,16 @@ static int layout_workspace(const HgPlan* plan, int B, int T, int precision, voi
   ws->mel.a0 = p + off;
   ws->mel.a1 = precision == HG_PREC_FP32 ? p + off + mplane : nullptr;
   off += mb;
+  if (concurrent_eligible(plan, B, T, precision)) {
+    for (int j = 0; j + 1 < c.num_kernels; ++j) {
+      ws->FB[j] = reinterpret_cast<float*>(p + off); off += fb;
+      for (int i = 0; i < 2; ++i) {
+        ws->AB[j][i].a0 = p + off;
+        ws->AB[j][i].a1 = precision == HG_PREC_FP32 ? p + off + plane : nullptr;
+        off += ab;
+      }
+    }
+  }
   ws->bytes = off + 4096;  // the folded pair kernel's input map may read (and discard) a few rows past an operand buffer
   return HG_OK;
 }
@@ -1372,6 +1410,18 @@ extern "C" int hg_forward_launches(const HgPlan* plan, int B, int T, int precisi
 
 // ------------------------------------------------------------------------------------------------
 // Generator.forward — hifi/models.py:185-201
+static int ensure_side_streams(HgPlan* plan, int n) {
+  if (!plan->ev_fork && cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming) != cudaSuccess)
+    return fail(HG_ECUDA, "cudaEventCreate: %s", cudaGetErrorString(cudaGetLastError()));
+  for (int j = 0; j <= n; ++j)
+    if (!plan->ev_done[j] && cudaEventCreateWithFlags(&plan->ev_done[j], cudaEventDisableTiming) != cudaSuccess)
+      return fail(HG_ECUDA, "cudaEventCreate: %s", cudaGetErrorString(cudaGetLastError()));
+  for (int j = 0; j < n; ++j)
+    if (!plan->side_stream[j] && cudaStreamCreateWithFlags(&plan->side_stream[j], cudaStreamNonBlocking) != cudaSuccess)
+      return fail(HG_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(cudaGetLastError()));
+  return HG_OK;
+}
+
 extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC, int64_t sT, int B, int T, void* out,
                           int out_dtype, float out_scale, int precision, void* workspace, size_t workspace_bytes,
                           void* stream) {
@@ -1392,6 +1442,15 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
   const int fmt = a_fmt_of(precision);
   const int U = c.num_upsamples, K = c.num_kernels, D = rb_dilations(c);
   const float slope = 0.1f;  // LRELU_SLOPE, hifi/models.py:9
+  // short inputs: the ResBlocks of a stage on separate streams (concurrent_eligible above); per-launch profiling and
+  // the whole-block kernel keep the single-stream schedule
+  const bool conc_any = concurrent_eligible(plan, B, T, precision) && !g_prof && !plan->fuse_blocks;
+  std::unique_lock<std::mutex> side_lock(plan->side_mutex, std::defer_lock);
+  if (conc_any) {
+    side_lock.lock();
+    if ((rc = ensure_side_streams(plan, K - 1))) return rc;
+  }
+  auto cuda_ok = [&](cudaError_t ce, const char* what) { return ce == cudaSuccess ? HG_OK : fail(HG_ECUDA, "%s: %s", what, cudaGetErrorString(ce)); };
 
   prof_mark(-2);
   // mel [B,80,T] (any strides) -> channels-last operand
@@ -1420,8 +1479,18 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
       if ((rc = run_layer(plan, up, precision, B, L, ws.A[a_cur], ep, st))) return rc;
     }
     L = (L - 1) * up.stride - 2 * up.pad + up.k;
+    const bool conc = conc_any && concurrent_stage(plan, static_cast<long long>(B) * L * up.cout);
+    if (conc) {  // fork: every block starts from the upsampler's output
+      if ((rc = cuda_ok(cudaEventRecord(plan->ev_fork, st), "cudaEventRecord"))) return rc;
+      for (int j = 1; j < K; ++j)
+        if ((rc = cuda_ok(cudaStreamWaitEvent(plan->side_stream[j - 1], plan->ev_fork, 0), "cudaStreamWaitEvent"))) return rc;
+    }
     // xs = sum_j resblocks[i*K+j](x) ; x = xs / K   :190-196
     for (int j = 0; j < K; ++j) {
+      // block j's stream and private buffers (index 0 = the shared stage input); single-stream schedule: everything shared
+      cudaStream_t sj = (conc && j > 0) ? plan->side_stream[j - 1] : st;
+      float* const Fj = (conc && j > 0) ? ws.FB[j - 1] : ws.F[1];
+      const OperandBuf Aj[3] = {ws.A[0], (conc && j > 0) ? ws.AB[j - 1][0] : ws.A[1], (conc && j > 0) ? ws.AB[j - 1][1] : ws.A[2]};
       ChainTiling ct;
       if (c.resblock_type == 1 && chain_fusable(plan, &LY[li], &LY[li + D], D, precision, &ct)) {
         // the whole ResBlock in one launch (conv_chain_tc.cu): x and the operand stay on chip between its pairs;
@@ -1460,8 +1529,8 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
           // xt = c1(leaky_relu(x)); only leaky_relu(xt) is consumed  :90-92
           const int a_t = 2;
           EpiParams ep; memset(&ep, 0, sizeof(ep));
-          ep.out_a0 = ws.A[a_t].a0; ep.out_a1 = ws.A[a_t].a1; ep.slope = slope;
-          if ((rc = run_layer(plan, LY[li + m], precision, B, L, ws.A[a_in], ep, st))) return rc;
+          ep.out_a0 = Aj[a_t].a0; ep.out_a1 = Aj[a_t].a1; ep.slope = slope;
+          if ((rc = run_layer(plan, LY[li + m], precision, B, L, Aj[a_in], ep, sj))) return rc;
           a_conv_in = a_t;
         }
         // x = c2(xt) + x  :93-94 (ResBlock2: x = c(leaky_relu(x)) + x  :136-138)
@@ -1470,9 +1539,9 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
         // next operand buffer must differ from the one this conv reads (neighbouring CTAs read halos)
         const int a_next = (a_conv_in == 1) ? 2 : 1;
         if (!last_pair) {
-          ep.out_x = ws.F[1]; ep.out_a0 = ws.A[a_next].a0; ep.out_a1 = ws.A[a_next].a1;
+          ep.out_x = Fj; ep.out_a0 = Aj[a_next].a0; ep.out_a1 = Aj[a_next].a1;
           a_in = a_next;
-          res = ws.F[1];
+          res = Fj;
         } else {
           // MRF combine fused into the block's last epilogue  :193-196
           if (j > 0) ep.acc_in = ws.F[2];
@@ -1484,23 +1553,29 @@ extern "C" int hg_forward(HgPlan* plan, const float* mel, int64_t sB, int64_t sC
               ep.out_x = ws.F[1];  // conv_post applies its own leaky_relu(0.01)  :197
               x_final = ws.F[1];
             } else {
-              ep.out_a0 = ws.A[a_next].a0; ep.out_a1 = ws.A[a_next].a1;
-              a_cur = a_next;
+              // concurrent schedule: the last block reads its private buffers, so the stage output can always go to A[1]
+              const int a_out = conc ? 1 : a_next;
+              ep.out_a0 = ws.A[a_out].a0; ep.out_a1 = ws.A[a_out].a1;
+              a_cur = a_out;
             }
           }
+          // join the MRF chain: this epilogue reads block j-1's sum (and, for the last block, writes buffers block 0 used)
+          if (conc && j > 0 && (rc = cuda_ok(cudaStreamWaitEvent(sj, plan->ev_done[j - 1], 0), "cudaStreamWaitEvent"))) return rc;
         }
         if (fold_ok && (!pair_ok || fold_pays(plan, l2, ep.acc_in != nullptr))) {
           // ... with F = 128 / C time rows folded into the MMA's N dimension  (conv_pair_fold.cu)
-          if ((rc = run_pair_fold(plan, LY[li + m], l2, ft, B, L, ws.A[a_conv_in], ep, slope, st))) return rc;
+          if ((rc = run_pair_fold(plan, LY[li + m], l2, ft, B, L, Aj[a_conv_in], ep, slope, sj))) return rc;
         } else if (fused) {
           // c1 and c2 in one kernel; xt never leaves shared memory  (conv_pair_tc.cu)
-          if ((rc = run_pair(plan, LY[li + m], l2, pt, B, L, ws.A[a_conv_in], ep, slope, st))) return rc;
-        } else if ((rc = run_layer(plan, l2, precision, B, L, ws.A[a_conv_in], ep, st))) {
+          if ((rc = run_pair(plan, LY[li + m], l2, pt, B, L, Aj[a_conv_in], ep, slope, sj))) return rc;
+        } else if ((rc = run_layer(plan, l2, precision, B, L, Aj[a_conv_in], ep, sj))) {
           return rc;
         }
       }
       li += c.resblock_type == 1 ? 2 * D : D;
+      if (conc && (rc = cuda_ok(cudaEventRecord(plan->ev_done[j], sj), "cudaEventRecord"))) return rc;
     }
+    if (conc && (rc = cuda_ok(cudaStreamWaitEvent(st, plan->ev_done[K - 1], 0), "cudaStreamWaitEvent"))) return rc;  // join
   }
   // x = tanh(conv_post(leaky_relu(x)))  :197-199  (+ optional int16 tail, hifiapi.py:50-51)
   const Layer& post = LY.back();

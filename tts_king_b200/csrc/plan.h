@@ -100,6 +100,8 @@ class TensorMapCache {
 
 }  // namespace hg
 
+namespace hg { constexpr int kMaxSideStreams = 7; }  // resblock kernels per stage - 1 (HG_MAX_KERNELS = 8)
+
 struct HgPlan {
   HgConfig cfg;
   int device = 0;
@@ -130,4 +132,11 @@ struct HgPlan {
   std::vector<int> stack_act;
   std::vector<float> stack_slope;
   hg::TensorMapCache maps;
+  // short inputs: the ResBlocks of a stage whose activations hold at most concurrent_elems elements run on separate
+  // streams (they only meet in the MRF sum), api.cu::hg_forward.  Streams / events are created on first use and owned by the plan; `side_mutex`
+  // serialises the enqueue of two such forwards on one plan (events are re-recorded per stage).
+  long long concurrent_elems = 2560 * 1024;  // HG_CONCURRENT_KELEMS (in units of 1024 elements; 0 switches it off)
+  cudaStream_t side_stream[hg::kMaxSideStreams] = {};
+  cudaEvent_t ev_fork = nullptr, ev_done[hg::kMaxSideStreams + 1] = {};
+  std::mutex side_mutex;
 };
