@@ -492,7 +492,7 @@ def main():
         roofline = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "traffic": traffic, "traffic_note": "DRAM bytes per step summed over the tcgen05 launches (ncu), not per launch",
                     "hbm_floor_ms": (traffic / (float(peaks.get("hbm_gbs", 6555.8)) * 1e9) * 1e3) if traffic else None,
-                    "tensor_floor_ms": tc_flops / (peak * 1e12) * 1e3, "measured_ms": tc_ms, "kernel": "conv_tc2_kernel + conv_pair_tc_kernel + conv_tc_kernel (tcgen05 implicit-GEMM convs, all 59 launches of a step)",
+                    "tensor_floor_ms": tc_flops / (peak * 1e12) * 1e3, "measured_ms": tc_ms, "kernel": "conv_tc2_kernel + conv_pair_fold_kernel + conv_pair_tc_kernel + conv_tc_kernel (tcgen05 implicit-GEMM convs, all 59 launches of a step)",
                     "share_of_step": tc_ms / all_ms if all_ms else None, "peak_source": peaks["_source"] + " sustained bf16",
                     "mma_passes_per_product": mult,
                     "per_layer": {"sum_of_launch_rooflines_ms": roof_ms, "sum_of_launch_times_ms": all_ms,
