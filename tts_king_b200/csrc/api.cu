@@ -175,22 +175,37 @@ static int make_operand_map(HgPlan* plan, const void* ptr, int L, int B, int cpi
 //   kind 0: fp32, 32 columns, 128B swizzle  (fused-pair residual tiles)
 //   kind 1: fp32, 16 columns,  64B swizzle  (conv_tc residual in / x out)
 //   kind 2: bf16, 16 columns,  32B swizzle  (conv_tc operand copies out)
-static int make_tile_map(HgPlan* plan, const void* ptr, int L, int B, int c, int kind, CUtensorMap* out) {
-  MapKey key(ptr, L, B, c, -(kind + 1), 32);
+// rstride > 1: the phase-major 4-D view [B][L / rstride][rstride][c] of a polyphase ConvTranspose1d's output (L is a
+// multiple of rstride); a box is 32 rows of ONE phase
+static int make_tile_map(HgPlan* plan, const void* ptr, int L, int B, int c, int kind, CUtensorMap* out, int rstride = 1) {
+  MapKey key(ptr, L, B, c, -(kind + 1), 32 * rstride);
   if (plan->maps.get(key, out)) return HG_OK;
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(HG_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
   const int esz = kind == 2 ? 2 : 4;
   const int cols = kind == 0 ? 32 : 16;
-  cuuint64_t dims[3] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(B)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(c) * esz, static_cast<cuuint64_t>(L) * c * esz};
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(cols), 32, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapDataType dt = kind == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapSwizzle sw = kind == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : kind == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   CUtensorMap m;
-  CUresult r = enc(&m, kind == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
-                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   kind == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : kind == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r;
+  if (rstride > 1) {
+    if (L % rstride) return fail(HG_ESTATE, "internal: phase-major map over %d rows, stride %d", L, rstride);
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(rstride), static_cast<cuuint64_t>(L / rstride),
+                          static_cast<cuuint64_t>(B)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(c) * esz, static_cast<cuuint64_t>(rstride) * c * esz,
+                             static_cast<cuuint64_t>(L) * c * esz};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(cols), 1, 32, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    r = enc(&m, dt, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(B)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(c) * esz, static_cast<cuuint64_t>(L) * c * esz};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(cols), 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    r = enc(&m, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   if (r != CUDA_SUCCESS) return fail(HG_ECUDA, "cuTensorMapEncodeTiled (tile kind %d) failed (%d)", kind, static_cast<int>(r));
   plan->maps.put(key, m);
   *out = m;
@@ -313,6 +328,7 @@ static void init_plan_env(HgPlan* p, int device) {
   p->fuse_pairs = env_int("HG_FUSE_PAIRS", 1) != 0;
   p->fold_pairs = env_int("HG_FOLD", 1) != 0;
   p->tile_alternate = env_int("HG_TILE_ORDER", 1) != 0;
+  p->epi_tma_convt = env_int("HG_EPI_TMA_CONVT", 1) != 0;
   p->concurrent_elems = static_cast<long long>(env_int("HG_CONCURRENT_KELEMS", 2560)) * 1024;
   p->fold_force = env_int("HG_FOLD", 1) == 2;
   // Off by default: measured on B200 (16 x 800 frames) the fused ResBlock is SLOWER than its three fused pairs
@@ -782,7 +798,9 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
     const bool split = precision == HG_PREC_FP32;
     // TMA epilogue for same-length convs without MRF accumulate (68 of the 78 layers of V1); its
     // per-warp slot holds the residual-in, x-out and operand-out tiles the layer actually uses
-    bool tma_epi = plan->epi_tma && l.kind == L_CONV && !epi.acc_in && epi.post_div <= 0.f && l.cout % 16 == 0 && !l.n_store;
+    // ... and for the polyphase upsamplers, whose phases are row-strided boxes of the output (HG_EPI_TMA_CONVT=0: generic)
+    const bool convt_tma = l.kind == L_CONVT && plan->epi_tma_convt && !epi.res && l.stride > 1 && L_out % l.stride == 0;
+    bool tma_epi = plan->epi_tma && (l.kind == L_CONV || convt_tma) && !epi.acc_in && epi.post_div <= 0.f && l.cout % 16 == 0 && !l.n_store;
     int slot = 2048;  // generic epilogue: one 32x16 fp32 transpose tile per warp
     if (tma_epi) {
       slot = (epi.res ? 2048 : 0) + (epi.out_x ? 2048 : 0) + (epi.out_a0 ? (split ? 2048 : 1024) : 0);
@@ -867,12 +885,15 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
       p.epi_slot_bytes = slot;
       if (tma_epi) {
         p.epi_tma = 1;
+        const int rs = l.kind == L_CONVT ? l.stride : 1;
+        const int Lo = static_cast<int>(L_out);
+        if (l.kind == L_CONVT) { p.out_cmod = l.cout; p.out_rstride = l.stride; p.out_roff = -l.pad; }
         if (epi.res) { p.has_res = 1; if ((rc = make_tile_map(plan, epi.res, L_in, B, l.cout, 1, &maps[2]))) return rc; }
-        if (epi.out_x) { p.has_x = 1; if ((rc = make_tile_map(plan, epi.out_x, L_in, B, l.cout, 1, &maps[3]))) return rc; }
+        if (epi.out_x) { p.has_x = 1; if ((rc = make_tile_map(plan, epi.out_x, Lo, B, l.cout, 1, &maps[3], rs))) return rc; }
         if (epi.out_a0) {
           p.has_a = 1;
-          if ((rc = make_tile_map(plan, epi.out_a0, L_in, B, l.cout, 2, &maps[4]))) return rc;
-          if (split && (rc = make_tile_map(plan, epi.out_a1, L_in, B, l.cout, 2, &maps[5]))) return rc;
+          if ((rc = make_tile_map(plan, epi.out_a0, Lo, B, l.cout, 2, &maps[4], rs))) return rc;
+          if (split && (rc = make_tile_map(plan, epi.out_a1, Lo, B, l.cout, 2, &maps[5], rs))) return rc;
         }
       }
       const int grid = std::min(p.total_work, plan->sm_count * std::max(1, plan->ctas_per_sm));

@@ -531,6 +531,10 @@ struct TcConvParams {
   int has_res, has_x, has_a;  // what the TMA epilogue reads / writes (maps are kernel arguments)
   int has_acc;                // conv_tc2 only: the MRF running sum is a second TMA-loaded input tile
   int epi_slot_bytes;         // shared memory per epilogue warp (TMA: res | x | a_hi | a_lo tiles; generic: 2 KB)
+  // TMA epilogue of a polyphase ConvTranspose1d: GEMM column n = phase * out_cmod + channel, GEMM row q lands on output
+  // row q * out_rstride + phase + out_roff.  The output maps are 4-D views [item][L_out / stride][stride][C], in which the
+  // 32 rows of an item (one phase) are a plain box.  out_cmod = 0: same-length conv, 3-D maps.
+  int out_cmod, out_rstride, out_roff;
   int desc_mode;  // how a tap's row shift enters the UMMA descriptor (see conv_tc.cu)
   long long* dbg;       // optional [grid][8] cycle counters (HG_TC_DEBUG_TIMING): MMA-warp wait breakdown
   RaggedPrefix rag;     // ragged batch: compacted tile index space (n == 0: dense)

@@ -355,8 +355,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
         }
         fence_proxy_async();  // generic-proxy writes of the tiles -> visible to the TMA unit
         __syncwarp();
-        if (lane == 0) {
-          const int row0 = m0 + ms * 128 + quarter * 32;
+        const int row0 = m0 + ms * 128 + quarter * 32;
+        if (p.out_cmod) {
+          // polyphase ConvTranspose1d: this item is one phase ph of 32 GEMM rows q; output row q*s + ph + roff =
+          // (q + dq)*s + ph2 with dq = floor((ph + roff) / s) — a box of the phase-major view.  Rows past the end of the
+          // sequence are clipped by the TMA unit; a NEGATIVE start coordinate is an illegal instruction for a TMA
+          // store, so the one item per phase and batch item that begins before row 0 stores its rows with plain
+          // stores (each lane its own row, read back from the staged tiles).
+          const int ph = n0 / p.out_cmod, col0 = n0 - ph * p.out_cmod;
+          const int t = ph + p.out_roff;
+          const int dq = t >= 0 ? t / p.out_rstride : -((-t + p.out_rstride - 1) / p.out_rstride);
+          const int ph2 = t - dq * p.out_rstride;
+          if (row0 + dq >= 0) {
+            if (lane == 0) {
+              if (p.has_x) tma_store_4d(&map_x, xb, col0, ph2, row0 + dq, b);
+              if (p.has_a) {
+                tma_store_4d(&map_ahi, ab_hi, col0, ph2, row0 + dq, b);
+                if (SPLIT) tma_store_4d(&map_alo, ab_lo, col0, ph2, row0 + dq, b);
+              }
+              tma_store_commit();
+            }
+          } else {
+            const long long orow = static_cast<long long>(row0 + lane) * p.out_rstride + t;  // this lane's output row
+            const long long off = static_cast<long long>(b) * p.epi.out_batch_stride + orow * p.out_cmod + col0;
+            if (orow >= 0 && (orow + 1) * p.out_cmod <= p.epi.out_extent) {
+              if (p.has_x) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  *reinterpret_cast<float4*>(p.epi.out_x + off + 4 * q) = *reinterpret_cast<const float4*>(xb + lane * 16 + ((q ^ swz64) << 2));
+              }
+              if (p.has_a) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                  *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.epi.out_a0) + off + 8 * q) =
+                      *reinterpret_cast<const uint4*>(ab_hi + lane * 32 + ((q ^ swz32) << 4));
+                  if (SPLIT)
+                    *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.epi.out_a1) + off + 8 * q) =
+                        *reinterpret_cast<const uint4*>(ab_lo + lane * 32 + ((q ^ swz32) << 4));
+                }
+              }
+            }
+            __syncwarp();  // the tiles are free again once every lane has read its row
+          }
+        } else if (lane == 0) {
           if (p.has_x) tma_store_3d(&map_x, xb, n0, row0, b);
           if (p.has_a) {
             tma_store_3d(&map_ahi, ab_hi, n0, row0, b);
