@@ -128,6 +128,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint64_t* w_full = bars + 28;         // [stages] (leader's)
   uint64_t* w_empty = w_full + p.stages;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_empty + p.stages);
+  // [N_T] bias: the epilogue's same-address float4 loads cost four L1 wavefronts each from global memory — as much as
+  // the operand tile a c1 layer stores — and one as a shared-memory broadcast
+  float* bias_s = reinterpret_cast<float*>(tmem_ptr_smem + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -142,6 +145,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (p.has_acc) prefetch_tensormap(&map_acc);
     if (p.has_x) prefetch_tensormap(&map_x);
     if (p.has_a) prefetch_tensormap(&map_ahi);
+  }
+  if (warp == 2) {  // a weight, not a product of the previous launch: may be read before griddepcontrol.wait
+    for (int i = lane; i < N_T / 4; i += 32) reinterpret_cast<float4*>(bias_s)[i] = __ldg(reinterpret_cast<const float4*>(p.epi.bias) + i);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -258,6 +264,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int e = warp - 3;
     const int quarter = warp & 3;
     const int sub = e >> 2;
+    const uint32_t bias_a = smem_u32(bias_s);
     uint8_t* slot = epi_smem + e * p.epi_slot_bytes;
     // slot: [residual in 2 KB] [MRF running sum in 2 KB] [x out 2 KB] [operand out 1 KB], each only if used
     const float* rb = reinterpret_cast<const float*>(slot);
@@ -308,7 +315,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float4 bb = *reinterpret_cast<const float4*>(p.epi.bias + c0 + 4 * q);
+          const float4 bb = lds128(bias_a + (c0 + 4 * q) * 4);
           v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
         }
         if (has_in) {
@@ -393,7 +400,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 size_t conv_tc2_smem_bytes(int n_t, int slab_rows, int nbuf, int stages, int epi_slot_bytes) {
   size_t slab = (static_cast<size_t>(nbuf) * slab_rows * 128 + 1023) & ~size_t(1023);
   return 1024 + slab + static_cast<size_t>(stages) * (n_t / 2) * 128 + static_cast<size_t>(kTc2EpiWarps) * epi_slot_bytes +
-         (28 + 2 * stages) * 8 + 16;
+         (28 + 2 * stages) * 8 + 16 + 1024;
 }
 
 template <int N_T, int MS>
