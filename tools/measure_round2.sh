@@ -13,6 +13,9 @@ timeout 300 python tools/profile_config.py v2_narrow 16 800 bf16 > $O/r2_${TAG}_
 # launch list of one forward (61 launches; the first forward is warm-up): per-launch time and DRAM bytes
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
   --launch-skip 61 --launch-count 61 --csv --log-file $O/r2_${TAG}_ncu_launches_bf16.csv python tools/ncu_one_forward.py bf16 > $O/ncu_launches.log 2>&1
+# the same launch list without ncu's L2 flush between kernels: the DRAM traffic the step really has (profiles/r2_tile_order_l2.md)
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none \
+  --launch-skip 61 --launch-count 61 --csv --log-file $O/r2_${TAG}_ncu_launches_bf16_in_situ.csv python tools/ncu_one_forward.py bf16 > $O/ncu_launches2.log 2>&1
 # the same pass over the bench command itself (the driver's profile convention): first 400 launches
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2_${TAG}_ncu_launches_bench_cmd.csv \
   python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline > $O/ncu_bench_cmd.log 2>&1
