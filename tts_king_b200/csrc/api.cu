@@ -328,6 +328,7 @@ static void init_plan_env(HgPlan* p, int device) {
   p->fuse_pairs = env_int("HG_FUSE_PAIRS", 1) != 0;
   p->fold_pairs = env_int("HG_FOLD", 1) != 0;
   p->tile_alternate = env_int("HG_TILE_ORDER", 1) != 0;
+  p->tc2_in_bufs = env_int("HG_TC2_INBUFS", 2) == 1 ? 1 : 2;
   p->epi_tma_convt = env_int("HG_EPI_TMA_CONVT", 1) != 0;
   p->concurrent_elems = static_cast<long long>(env_int("HG_CONCURRENT_KELEMS", 2560)) * 1024;
   p->fold_force = env_int("HG_FOLD", 1) == 2;
@@ -811,7 +812,11 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
     // (its TMA epilogue also takes the MRF running sum as a second input tile, so the last conv of a
     // ResBlock — xs += x, / num_kernels — stays on this path)
     const bool tma_epi2 = plan->epi_tma && l.kind == L_CONV && l.cout % 16 == 0 && !l.n_store;
-    const int slot2 = std::max(1024, (epi.res ? 2048 : 0) + (epi.acc_in ? 2048 : 0) + (epi.out_x ? 2048 : 0) + (epi.out_a0 ? 1024 : 0));
+    // conv_tc2.cu keeps TWO residual tiles in flight per epilogue warp where the layer only has a residual input; with
+    // the MRF running sum as a second input the doubled slot would cost the weight ring its depth (HG_TC2_INBUFS=1: one)
+    const int in_tile = (epi.res ? 2048 : 0) + (epi.acc_in ? 2048 : 0);
+    const int in_bufs = (plan->tc2_in_bufs == 2 && epi.res && !epi.acc_in) ? 2 : 1;
+    const int slot2 = std::max(1024, in_bufs * in_tile + (epi.out_x ? 2048 : 0) + (epi.out_a0 ? 1024 : 0));
     if (plan->use_tc2 && tma_epi2 && !split && l.n_blocks == 1 && l.kc == 64 && (l.n_tile == 128 || l.n_tile == 256) &&
         !choose_tiling(plan, l, split, tma_epi ? slot : 2048).resident) {
       const int slot = slot2;  // shadows the single-CTA kernel's slot size inside this branch
@@ -837,7 +842,7 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
         p.min_off = min_off; p.slab_rows = slab_rows; p.box_rows = box_rows; p.nboxes = nboxes;
         p.nbuf = nbuf; p.stages = stages; p.n_blocks = 1;
         p.total_work = ragged_fill(&p.rag, rag, B, rows, 2 * ms * 128);
-        p.epi = epi; p.epi_tma = 1; p.epi_slot_bytes = slot;
+        p.epi = epi; p.epi_tma = 1; p.epi_slot_bytes = slot; p.in_bufs = in_bufs;
         CUtensorMap maps[6];
         int rc = make_operand_map(plan, in.a0, L_in, B, l.cin_pad, 64, box_rows, &maps[0]);
         if (rc) return rc;

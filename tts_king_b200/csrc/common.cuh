@@ -530,6 +530,7 @@ struct TcConvParams {
   int epi_tma;     // 1: TMA epilogue (residual tiles loaded, x / operand tiles stored by TMA); 0: generic
   int has_res, has_x, has_a;  // what the TMA epilogue reads / writes (maps are kernel arguments)
   int has_acc;                // conv_tc2 only: the MRF running sum is a second TMA-loaded input tile
+  int in_bufs;                // conv_tc2 only: input (residual / running sum) tiles in flight per epilogue warp, 1 or 2
   int epi_slot_bytes;         // shared memory per epilogue warp (TMA: res | x | a_hi | a_lo tiles; generic: 2 KB)
   // TMA epilogue of a polyphase ConvTranspose1d: GEMM column n = phase * out_cmod + channel, GEMM row q lands on output
   // row q * out_rstride + phase + out_roff.  The output maps are 4-D views [item][L_out / stride][stride][C], in which the

@@ -124,8 +124,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint64_t* slab_empty = bars + 4;      // [4]
   uint64_t* acc_full = bars + 8;        // [2]
   uint64_t* acc_empty = bars + 10;      // [2]  (leader's)
-  uint64_t* res_bar = bars + 12;        // [16]
-  uint64_t* w_full = bars + 28;         // [stages] (leader's)
+  uint64_t* res_bar = bars + 12;        // [16][2]: two input tiles in flight per epilogue warp
+  uint64_t* w_full = bars + 44;         // [stages] (leader's)
   uint64_t* w_empty = w_full + p.stages;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_empty + p.stages);
   // [N_T] bias: the epilogue's same-address float4 loads cost four L1 wavefronts each from global memory — as much as
@@ -154,7 +154,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       for (int i = 0; i < 4; ++i) { mbar_init(&slab_full[i], 1); mbar_init(&slab_empty[i], 1); }
       for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * kTc2EpiWarps); }
       for (int s = 0; s < p.stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-      for (int w = 0; w < kTc2EpiWarps; ++w) mbar_init(&res_bar[w], 1);
+      for (int w = 0; w < 2 * kTc2EpiWarps; ++w) mbar_init(&res_bar[w], 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -266,26 +266,35 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int sub = e >> 2;
     const uint32_t bias_a = smem_u32(bias_s);
     uint8_t* slot = epi_smem + e * p.epi_slot_bytes;
-    // slot: [residual in 2 KB] [MRF running sum in 2 KB] [x out 2 KB] [operand out 1 KB], each only if used
-    const float* rb = reinterpret_cast<const float*>(slot);
-    const float* accb = reinterpret_cast<const float*>(slot + (p.has_res ? 2048 : 0));
-    float* xb = reinterpret_cast<float*>(slot + (p.has_res ? 2048 : 0) + (p.has_acc ? 2048 : 0));
+    // slot: in_bufs x ([residual in 2 KB] [MRF running sum in 2 KB]) [x out 2 KB] [operand out 1 KB], each only if used.
+    // TWO input buffers where they fit: with one, every warp had a single 2 KB tile in flight and an item could not start before a
+    // whole HBM round trip — 16 warps x 512 elements per ~2.5 us is the 0.24 ms the residual-carrying C = 128 layers
+    // took for their 0.19 ms of HBM traffic.
+    const int in_bytes = (p.has_res ? 2048 : 0) + (p.has_acc ? 2048 : 0);
+    const uint32_t ib_mask = p.in_bufs == 2 ? 1u : 0u;
+    float* xb = reinterpret_cast<float*>(slot + p.in_bufs * in_bytes);
     const bool has_in = p.has_res || p.has_acc;
     uint8_t* ab_hi = reinterpret_cast<uint8_t*>(xb) + (p.has_x ? 2048 : 0);
     constexpr int ITEMS = MS * CHUNKS;
     const uint32_t acc_empty_leader0 = map_to_cta(&acc_empty[0], 0);
     const uint32_t acc_empty_leader1 = map_to_cta(&acc_empty[1], 0);
-    auto prefetch_res = [&](int work, int j) {  // lane 0 only
+    // lane 0's prefetch cursor: the next item (work, j) of this warp to request, and how many have been requested
+    int pf_work = pair, pf_j = sub, pf_n = 0;
+    auto prefetch_next = [&]() {  // lane 0 only
+      if (pf_work >= p.total_work) return;
       int b, m0;
-      tile_coords(work, b, m0);
-      const int ms = j / CHUNKS, c0 = (j - ms * CHUNKS) * 16;
-      mbar_arrive_expect_tx(&res_bar[e], (p.has_res ? 2048 : 0) + (p.has_acc ? 2048 : 0));
-      if (p.has_res) tma_load_3d(slot, &map_res, &res_bar[e], c0, m0 + ms * 128 + quarter * 32, b);
-      if (p.has_acc)
-        tma_load_3d(slot + (p.has_res ? 2048 : 0), &map_acc, &res_bar[e], c0, m0 + ms * 128 + quarter * 32, b);
+      tile_coords(pf_work, b, m0);
+      const int ms = pf_j / CHUNKS, c0 = (pf_j - ms * CHUNKS) * 16;
+      uint8_t* dst = slot + (pf_n & ib_mask) * in_bytes;
+      uint64_t* bar = &res_bar[2 * e + (pf_n & ib_mask)];
+      mbar_arrive_expect_tx(bar, in_bytes);
+      if (p.has_res) tma_load_3d(dst, &map_res, bar, c0, m0 + ms * 128 + quarter * 32, b);
+      if (p.has_acc) tma_load_3d(dst + (p.has_res ? 2048 : 0), &map_acc, bar, c0, m0 + ms * 128 + quarter * 32, b);
+      ++pf_n;
+      if (pf_j + 4 < ITEMS) pf_j += 4; else { pf_work += npairs; pf_j = sub; }
     };
-    uint32_t res_uses = 0;
-    if (has_in && lane == 0 && sub < ITEMS && pair < p.total_work) prefetch_res(pair, sub);
+    uint32_t n_item = 0;  // items consumed by this warp
+    if (has_in && lane == 0 && sub < ITEMS) { prefetch_next(); if (p.in_bufs == 2) prefetch_next(); }
     const uint32_t swz64 = (lane >> 1) & 3, swz32 = (lane >> 2) & 1;
     int it = 0;
     for (int work = pair; work < p.total_work; work += npairs, ++it) {
@@ -319,8 +328,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
         }
         if (has_in) {
-          mbar_wait(&res_bar[e], res_uses & 1);
-          ++res_uses;
+          const uint32_t ib = n_item & ib_mask;
+          mbar_wait(&res_bar[2 * e + ib], (p.in_bufs == 2 ? n_item >> 1 : n_item) & 1);
+          ++n_item;
+          const float* rb = reinterpret_cast<const float*>(slot + ib * in_bytes);
+          const float* accb = reinterpret_cast<const float*>(slot + ib * in_bytes + (p.has_res ? 2048 : 0));
           if (p.has_res) {  // x = xt + x   (hifi/models.py:94)
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -338,10 +350,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           }
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) {
-            if (j + 4 < ITEMS) prefetch_res(work, j + 4);
-            else if (work + npairs < p.total_work) prefetch_res(work + npairs, sub);
-          }
+          if (lane == 0) prefetch_next();  // into the buffer just read: the item after next
         }
         if (p.epi.post_div == 3.f) {  // x = xs / num_kernels   (:196), V1's three kernels: common.cuh::div3_rn
 #pragma unroll
@@ -400,7 +409,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 size_t conv_tc2_smem_bytes(int n_t, int slab_rows, int nbuf, int stages, int epi_slot_bytes) {
   size_t slab = (static_cast<size_t>(nbuf) * slab_rows * 128 + 1023) & ~size_t(1023);
   return 1024 + slab + static_cast<size_t>(stages) * (n_t / 2) * 128 + static_cast<size_t>(kTc2EpiWarps) * epi_slot_bytes +
-         (28 + 2 * stages) * 8 + 16 + 1024;
+         (44 + 2 * stages) * 8 + 16 + 1024;
 }
 
 template <int N_T, int MS>
