@@ -312,6 +312,18 @@ typedef struct HgFoldInfo {
 HG_API int hg_fold_info(int C, int k, int d1, int L, HgFoldInfo* info);
 
 /*
+ * Host-side view of the streamed-weight ring of the time-folded pair kernel (conv_pair_fold.cu::FoldRingPlan<k, period>),
+ * evaluated by the same constexpr functions the kernel is compiled from: for tap `tap` of a conv whose position in the
+ * ring order G1(0) G1(1) G2(0) G1(2) ... has parity `conv_parity`, the shared-memory slot, the mbarrier parity the
+ * consumer waits for, and whether the tap is also copied into the mirror slot behind the ring.  *slots receives the
+ * number of weight blocks held in shared memory.  Lets the CPU tests check that every slot's barrier is used with
+ * strictly alternating parity and that every run of two consecutive taps is contiguous.  Returns HG_EINVAL for a
+ * (k, period) the kernel is not instantiated for.
+ */
+HG_API int hg_fold_ring_query(int k, int period, int tap, int conv_parity, int32_t* slot, int32_t* parity, int32_t* mirror,
+                              int32_t* slots);
+
+/*
  * Debug / bring-up: runs the tcgen05 descriptor self-test (shifted-row UMMA descriptors against a
  * CUDA-core reference) and writes a report into `buf`.  Returns the number of failing cases.
  */

@@ -158,3 +158,63 @@ def test_fold_falls_back_where_it_does_not_apply():
     assert fold_info(128, 3, 1, 1000).fusable == 0   # only C = 16 / 32 / 64
     assert fold_info(16, 7, 3, 1004).fusable == 0    # 1004 % 8 != 0
     assert fold_info(32, 11, 5, 1002).fusable == 0   # 1002 % 4 != 0
+
+
+RING_CASES = [(5, 5), (7, 7), (7, 5), (7, 4), (9, 6), (9, 5), (9, 4), (11, 6), (11, 5), (11, 4)]
+
+
+def _ring(k, s, tap, cpar):
+    slot, par, mir, slots = (ctypes.c_int32() for _ in range(4))
+    _native.check(_native.lib().hg_fold_ring_query(k, s, tap, cpar, ctypes.byref(slot), ctypes.byref(par), ctypes.byref(mir),
+                                                  ctypes.byref(slots)))
+    return slot.value, par.value, bool(mir.value), slots.value
+
+
+@pytest.mark.parametrize("k,s", RING_CASES)
+def test_streamed_weight_ring_plan(k, s):
+    """The streamed-weight ring of the folded pair kernel has a COMPILE-TIME period (conv_pair_fold.cu::FoldRingPlan):
+    slot, barrier and parity of every tap are constants of the unrolled code plus one run-time bit (the parity of the
+    conv's position in the ring order).  hg_fold_ring_query evaluates the kernel's own constexpr functions; this test
+    replays producer and consumer over many convs with the mbarrier phase rule (a wait with parity P passes once the
+    phase of parity P has completed, phases complete strictly in order):
+      * every use of a slot's `full` barrier waits for exactly the next phase (parities alternate 0, 1, 0, ... per
+        slot), so a consumer can never pass on a stale phase, and the producer's `empty` wait (parity ^ 1) passes at
+        once for the first fill and thereafter needs exactly the previous occupant's release;
+      * the two taps of every MMA group's run are contiguous in shared memory — neighbouring slots, or slot S - 1
+        followed by the mirror slot, which then holds the right tap;
+      * the blocks fit the slots the host allocates for that period."""
+    full_phase = [0] * s    # completed phases of w_full[slot]
+    empty_phase = [0] * s   # completed phases of w_empty[slot]
+    held = [None] * (s + 1)  # tap held by each physical slot (index s = the mirror)
+    slots_expected = s + (1 if k > s else 0)
+    for conv in range(9):  # G1(0) G1(1) G2(0) G1(2) ...: only the parity of the position enters
+        cpar = conv & 1
+        # producer: taps in order; consumer: group oi uses the run (oi - 1, oi) and then releases tap oi - 1
+        for tap in range(k):
+            slot, par, mirror, slots = _ring(k, s, tap, cpar)
+            assert slots == slots_expected and slot == tap % s
+            assert mirror == (k > s and tap >= s and tap % s == 0)
+            # producer waits for the release of the slot's previous occupant: phase (uses so far - 1) of w_empty
+            uses_so_far = full_phase[slot]
+            assert (par ^ 1) == ((uses_so_far - 1) & 1) if uses_so_far else (par ^ 1) == 1
+            assert empty_phase[slot] == uses_so_far, "the previous occupant must have been released before the refill"
+            held[slot] = tap
+            if mirror:
+                held[s] = tap
+            # consumer waits for this fill: it is phase `uses_so_far` of w_full, and the wait names exactly that parity
+            assert par == (uses_so_far & 1), (tap, slot, par, uses_so_far)
+            full_phase[slot] += 1
+            # MMA group `tap` (oi = tap >= 1) multiplies the run (tap - 1, tap): contiguous blocks
+            if tap >= 1:
+                first = (tap - 1) % s
+                second = first + 1  # physical slot right behind it (s = the mirror)
+                assert held[first] == tap - 1 and held[second] == tap, (tap, held)
+                empty_phase[first] += 1  # ... and releases tap - 1
+        empty_phase[(k - 1) % s] += 1  # the last group (oi = k) uses tap k - 1 alone and releases it
+
+
+def test_streamed_weight_ring_rejects_unknown_periods():
+    for k, s in ((11, 7), (7, 6), (5, 4), (3, 3), (11, 0)):
+        slot = ctypes.c_int32()
+        assert _native.lib().hg_fold_ring_query(k, s, 0, 0, ctypes.byref(slot), ctypes.byref(slot), ctypes.byref(slot),
+                                                ctypes.byref(slot)) != 0

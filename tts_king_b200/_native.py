@@ -108,6 +108,9 @@ def lib() -> ctypes.CDLL:
     L.hg_op_resblock1.restype = i
     L.hg_fold_info.argtypes = [i, i, i, i, ctypes.POINTER(HgFoldInfo)]
     L.hg_fold_info.restype = i
+    p32 = ctypes.POINTER(ctypes.c_int32)
+    L.hg_fold_ring_query.argtypes = [i, i, i, i, p32, p32, p32, p32]
+    L.hg_fold_ring_query.restype = i
     L.hg_layer_count.argtypes = [vp, ctypes.POINTER(i)]
     L.hg_layer_info.argtypes = [vp, i, i, ctypes.POINTER(HgLayerInfo)]
     L.hg_profile_launch_info.argtypes = [vp, i, ctypes.POINTER(HgLayerInfo)]

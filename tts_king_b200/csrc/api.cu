@@ -43,6 +43,7 @@ cudaError_t launch_conv_chain_tc(int c, const CUtensorMap& m, const CUtensorMap&
 size_t conv_fold_smem_bytes(int c, int slab_phase_bytes, int xt_phase_bytes, int t_bufs, int stages);
 bool conv_fold_has_kernel(int c, int k, int ring_period);
 int conv_fold_weight_slots(int k, int ring_period);
+bool conv_fold_ring_query(int k, int s, int tap, int cpar, int* slot, int* parity, int* mirror, int* slots);
 cudaError_t launch_conv_pair_fold(int c, int k, int ring_period, const CUtensorMap& m, const CUtensorMap& mr, const TcFoldParams& p,
                                   size_t smem, int grid, cudaStream_t st);
 }  // namespace hg
@@ -2153,6 +2154,16 @@ extern "C" int hg_fold_info(int C, int k, int d1, int L, HgFoldInfo* info) {
       o[2] = ops[i].b_blk; o[3] = ops[i].nblk; o[4] = ops[i].d_col; o[5] = ops[i].rel;
     }
   }
+  return HG_OK;
+}
+
+extern "C" int hg_fold_ring_query(int k, int period, int tap, int conv_parity, int32_t* slot, int32_t* parity, int32_t* mirror,
+                                  int32_t* slots) {
+  if (!slot || !parity || !mirror || !slots) return fail(HG_EINVAL, "null output");
+  int a, b, c, d;
+  if (!conv_fold_ring_query(k, period, tap, conv_parity, &a, &b, &c, &d))
+    return fail(HG_EINVAL, "no streamed-weight kernel for k = %d, ring period %d (tap %d)", k, period, tap);
+  *slot = a; *parity = b; *mirror = c; *slots = d;
   return HG_OK;
 }
 

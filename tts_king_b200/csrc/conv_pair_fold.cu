@@ -561,6 +561,26 @@ bool conv_fold_has_kernel(int c, int k, int s) {
 // physical weight blocks of shared memory the (k, period) kernel uses
 int conv_fold_weight_slots(int k, int s) { return s == 0 ? 2 * k : s + (k > s ? 1 : 0); }
 
+// host-side view of FoldRingPlan<k, s> (hg_fold_ring_query): the constexpr functions the kernels are compiled from
+template <int K, int S>
+static void ring_query(int tap, int cpar, int* slot, int* parity, int* mirror, int* slots) {
+  using Plan = FoldRingPlan<K, S>;
+  *slot = tap % S;
+  *parity = static_cast<int>(Plan::parity(tap, static_cast<uint32_t>(cpar & 1)));
+  *mirror = (Plan::kMirror && tap >= S && tap % S == 0) ? 1 : 0;
+  *slots = Plan::kSlots;
+}
+bool conv_fold_ring_query(int k, int s, int tap, int cpar, int* slot, int* parity, int* mirror, int* slots) {
+  if (s <= 0 || tap < 0 || tap >= k || !conv_fold_has_kernel(64, k, s)) return false;
+#define HG_RING_CASE(KV, SV) if (k == KV && s == SV) { ring_query<KV, SV>(tap, cpar, slot, parity, mirror, slots); return true; }
+  HG_RING_CASE(5, 5)
+  HG_RING_CASE(7, 7) HG_RING_CASE(7, 5) HG_RING_CASE(7, 4)
+  HG_RING_CASE(9, 6) HG_RING_CASE(9, 5) HG_RING_CASE(9, 4)
+  HG_RING_CASE(11, 6) HG_RING_CASE(11, 5) HG_RING_CASE(11, 4)
+#undef HG_RING_CASE
+  return false;
+}
+
 template <int C, int K, int S>
 static cudaError_t launch_fold(const CUtensorMap& m, const CUtensorMap& mr, const TcFoldParams& p, size_t smem, int grid,
                                cudaStream_t st) {
