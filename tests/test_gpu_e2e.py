@@ -365,7 +365,7 @@ def test_multi_gpu_sharding_matches_single_gpu():
 
 @pytest.mark.parametrize("env", [{"HG_TC2": "0"}, {"HG_FUSE_PAIRS": "0"}, {"HG_EPI_TMA": "0"}, {"HG_FOLD": "0"}, {"HG_FOLD": "2"}, {"HG_PAD_NARROW": "0"}, {"HG_CHAIN": "1"},
                                  {"HG_TC2": "0", "HG_FUSE_PAIRS": "0", "HG_EPI_TMA": "0"}, {"HG_FORCE_FFMA": "1"},
-                                 {"HG_EPI_TMA_CONVT": "0"}, {"HG_TILE_ORDER": "0", "HG_CONCURRENT_KELEMS": "0"}])
+                                 {"HG_EPI_TMA_CONVT": "0"}, {"HG_TC2_CONVT": "0"}, {"HG_TILE_ORDER": "0", "HG_CONCURRENT_KELEMS": "0"}])
 def test_alternative_kernel_paths_keep_parity(env):
     """Every layer has more than one kernel path (CTA-pair / single-CTA tcgen05, fused / unfused
     ResBlock pairs, TMA / generic epilogue, CUDA-core).  Each combination must meet the same

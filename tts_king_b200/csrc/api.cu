@@ -330,6 +330,7 @@ static void init_plan_env(HgPlan* p, int device) {
   p->fold_pairs = env_int("HG_FOLD", 1) != 0;
   p->tile_alternate = env_int("HG_TILE_ORDER", 1) != 0;
   p->tc2_in_bufs = env_int("HG_TC2_INBUFS", 2) == 1 ? 1 : 2;
+  p->tc2_convt = env_int("HG_TC2_CONVT", 1) != 0;
   p->epi_tma_convt = env_int("HG_EPI_TMA_CONVT", 1) != 0;
   p->concurrent_elems = static_cast<long long>(env_int("HG_CONCURRENT_KELEMS", 2560)) * 1024;
   p->fold_force = env_int("HG_FOLD", 1) == 2;
@@ -812,13 +813,16 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
     // — whenever the single-CTA kernel could not keep the layer's weights resident in shared memory
     // (its TMA epilogue also takes the MRF running sum as a second input tile, so the last conv of a
     // ResBlock — xs += x, / num_kernels — stays on this path)
-    const bool tma_epi2 = plan->epi_tma && l.kind == L_CONV && l.cout % 16 == 0 && !l.n_store;
+    // ... and the polyphase upsamplers with several N blocks (N_total = stride * C_out): their weight stream per
+    // work item (N_T x K: 256 KB at ups.1) starves a single CTA's ring; the pair halves it per SM (HG_TC2_CONVT=0: off)
+    const bool convt2 = convt_tma && plan->tc2_convt && l.n_blocks > 1 && !epi.acc_in;
+    const bool tma_epi2 = plan->epi_tma && (l.kind == L_CONV || convt2) && l.cout % 16 == 0 && !l.n_store;
     // conv_tc2.cu keeps TWO residual tiles in flight per epilogue warp where the layer only has a residual input; with
     // the MRF running sum as a second input the doubled slot would cost the weight ring its depth (HG_TC2_INBUFS=1: one)
     const int in_tile = (epi.res ? 2048 : 0) + (epi.acc_in ? 2048 : 0);
     const int in_bufs = (plan->tc2_in_bufs == 2 && epi.res && !epi.acc_in) ? 2 : 1;
     const int slot2 = std::max(1024, in_bufs * in_tile + (epi.out_x ? 2048 : 0) + (epi.out_a0 ? 1024 : 0));
-    if (plan->use_tc2 && tma_epi2 && !split && l.n_blocks == 1 && l.kc == 64 && (l.n_tile == 128 || l.n_tile == 256) &&
+    if (plan->use_tc2 && tma_epi2 && !split && (l.n_blocks == 1 || convt2) && l.kc == 64 && (l.n_tile == 128 || l.n_tile == 256) &&
         !choose_tiling(plan, l, split, tma_epi ? slot : 2048).resident) {
       const int slot = slot2;  // shadows the single-CTA kernel's slot size inside this branch
       int min_off = l.tap_off[0], max_off = l.tap_off[0];
@@ -841,18 +845,21 @@ static int run_layer(HgPlan* plan, const Layer& l, int precision, int B, int L_i
         p.nc = l.nc; p.ntaps = l.ntaps;
         for (int j = 0; j < l.ntaps; ++j) p.tap_row[j] = l.tap_off[j] - min_off;
         p.min_off = min_off; p.slab_rows = slab_rows; p.box_rows = box_rows; p.nboxes = nboxes;
-        p.nbuf = nbuf; p.stages = stages; p.n_blocks = 1;
-        p.total_work = ragged_fill(&p.rag, rag, B, rows, 2 * ms * 128);
+        p.nbuf = nbuf; p.stages = stages; p.n_blocks = l.n_blocks;
+        p.total_work = ragged_fill(&p.rag, rag, B, rows, 2 * ms * 128) * l.n_blocks;
         p.epi = epi; p.epi_tma = 1; p.epi_slot_bytes = slot; p.in_bufs = in_bufs;
         CUtensorMap maps[6];
         int rc = make_operand_map(plan, in.a0, L_in, B, l.cin_pad, 64, box_rows, &maps[0]);
         if (rc) return rc;
-        if ((rc = make_weight_map(plan, l.w_hi, static_cast<long long>(l.nc) * l.ntaps * l.n_tile, l.n_tile / 2, &maps[1]))) return rc;
+        if ((rc = make_weight_map(plan, l.w_hi, static_cast<long long>(l.n_blocks) * l.nc * l.ntaps * l.n_tile, l.n_tile / 2, &maps[1]))) return rc;
         maps[2] = maps[3] = maps[4] = maps[5] = maps[0];
+        const int rs = l.kind == L_CONVT ? l.stride : 1;
+        const int Lo = static_cast<int>(L_out);
+        if (l.kind == L_CONVT) { p.out_cmod = l.cout; p.out_rstride = l.stride; p.out_roff = -l.pad; }
         if (epi.acc_in) { p.has_acc = 1; if ((rc = make_tile_map(plan, epi.acc_in, L_in, B, l.cout, 1, &maps[5]))) return rc; }
         if (epi.res) { p.has_res = 1; if ((rc = make_tile_map(plan, epi.res, L_in, B, l.cout, 1, &maps[2]))) return rc; }
-        if (epi.out_x) { p.has_x = 1; if ((rc = make_tile_map(plan, epi.out_x, L_in, B, l.cout, 1, &maps[3]))) return rc; }
-        if (epi.out_a0) { p.has_a = 1; if ((rc = make_tile_map(plan, epi.out_a0, L_in, B, l.cout, 2, &maps[4]))) return rc; }
+        if (epi.out_x) { p.has_x = 1; if ((rc = make_tile_map(plan, epi.out_x, Lo, B, l.cout, 1, &maps[3], rs))) return rc; }
+        if (epi.out_a0) { p.has_a = 1; if ((rc = make_tile_map(plan, epi.out_a0, Lo, B, l.cout, 2, &maps[4], rs))) return rc; }
         const int pairs = std::min(p.total_work, plan->sm_count / 2);
         const size_t smem = conv_tc2_smem_bytes(l.n_tile, slab_rows, nbuf, stages, slot);
         cudaError_t e = launch_conv_tc2(l.n_tile, ms, maps, p, smem, 2 * pairs, st);

@@ -169,10 +169,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   pdl_launch_dependents();
   if (warp != 0) pdl_wait();
 
-  // pair tile -> (batch item, first row of THIS CTA's 128*MS rows)
-  auto tile_coords = [&](int work, int& b, int& m0) {
+  // work item -> (N block, batch item, first row of THIS CTA's 128*MS rows); N blocks of one pair tile are consecutive
+  // work items (the polyphase upsamplers: N_total = stride * C_out), so their slab reloads hit L2
+  auto tile_coords = [&](int work, int& nblk, int& b, int& m0) {
+    nblk = work % p.n_blocks;
     int tile;
-    decode_tile(p.rag, p.tiles_per_item, work, b, tile);
+    decode_tile(p.rag, p.tiles_per_item, work / p.n_blocks, b, tile);
     m0 = tile * (2 * MS * 128) + static_cast<int>(rank) * (MS * 128);
   };
 
@@ -181,13 +183,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int work = pair; work < p.total_work; work += npairs) {
+        const int nblk = work % p.n_blocks;
         for (int c = 0; c < p.nc; ++c) {
           for (int t = 0; t < p.ntaps; ++t) {
             mbar_wait(&w_empty[stage], phase ^ 1);
             if (leader) mbar_arrive_expect_tx(&w_full[stage], 2 * STAGE_BYTES);
-            // packed image rows: ((chunk*ntaps + tap) * N_T + row); this CTA takes rows [rank*HALF_N, +HALF_N)
+            // packed image rows: (((n_blk*nc + chunk)*ntaps + tap) * N_T + row); this CTA takes rows [rank*HALF_N, +HALF_N)
             tma2_load_2d(wst + stage * STAGE_BYTES, &map_w, map_to_cta(&w_full[stage], 0), 0,
-                         (c * p.ntaps + t) * N_T + static_cast<int>(rank) * HALF_N);
+                         ((nblk * p.nc + c) * p.ntaps + t) * N_T + static_cast<int>(rank) * HALF_N);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -198,8 +201,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (lane == 0) {
       int buf = 0; uint32_t phase = 0;
       for (int work = pair; work < p.total_work; work += npairs) {
-        int b, m0;
-        tile_coords(work, b, m0);
+        int nblk, b, m0;
+        tile_coords(work, nblk, b, m0);
         for (int c = 0; c < p.nc; ++c) {
           mbar_wait(&slab_empty[buf], phase ^ 1);
           if (leader) mbar_arrive_expect_tx(&slab_full[buf], 2 * slab_bytes);
@@ -282,9 +285,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     int pf_work = pair, pf_j = sub, pf_n = 0;
     auto prefetch_next = [&]() {  // lane 0 only
       if (pf_work >= p.total_work) return;
-      int b, m0;
-      tile_coords(pf_work, b, m0);
-      const int ms = pf_j / CHUNKS, c0 = (pf_j - ms * CHUNKS) * 16;
+      int nblk, b, m0;
+      tile_coords(pf_work, nblk, b, m0);
+      const int ms = pf_j / CHUNKS, c0 = nblk * N_T + (pf_j - ms * CHUNKS) * 16;
       uint8_t* dst = slot + (pf_n & ib_mask) * in_bytes;
       uint64_t* bar = &res_bar[2 * e + (pf_n & ib_mask)];
       mbar_arrive_expect_tx(bar, in_bytes);
@@ -298,8 +301,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const uint32_t swz64 = (lane >> 1) & 3, swz32 = (lane >> 2) & 1;
     int it = 0;
     for (int work = pair; work < p.total_work; work += npairs, ++it) {
-      int b, m0;
-      tile_coords(work, b, m0);
+      int nblk, b, m0;
+      tile_coords(work, nblk, b, m0);
       const int ab = it & 1;
       const uint32_t tmem_acc = tmem_base + ab * ACC_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
       mbar_wait(&acc_full[ab], (it >> 1) & 1);
@@ -324,7 +327,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float4 bb = lds128(bias_a + (c0 + 4 * q) * 4);
+          const float4 bb = p.n_blocks == 1 ? lds128(bias_a + (c0 + 4 * q) * 4)
+                                            : *reinterpret_cast<const float4*>(p.epi.bias + nblk * N_T + c0 + 4 * q);
           v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
         }
         if (has_in) {
@@ -383,10 +387,43 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
-          const int row0 = m0 + ms * 128 + quarter * 32;
-          if (p.has_x) tma_store_3d(&map_x, xb, c0, row0, b);
-          if (p.has_a) tma_store_3d(&map_ahi, ab_hi, c0, row0, b);
+        const int row0 = m0 + ms * 128 + quarter * 32;
+        if (p.out_cmod) {
+          // polyphase ConvTranspose1d (conv_tc.cu has the same epilogue): this item is one phase ph of 32 GEMM rows q;
+          // output row q*s + ph + roff = (q + dq)*s + ph2 — a box of the phase-major 4-D view.  A negative start
+          // coordinate faults in a TMA store: the one item per phase that begins before row 0 uses plain stores.
+          const int n0 = nblk * N_T + c0;
+          const int ph = n0 / p.out_cmod, col0 = n0 - ph * p.out_cmod;
+          const int t = ph + p.out_roff;
+          const int dq = t >= 0 ? t / p.out_rstride : -((-t + p.out_rstride - 1) / p.out_rstride);
+          const int ph2 = t - dq * p.out_rstride;
+          if (row0 + dq >= 0) {
+            if (lane == 0) {
+              if (p.has_x) tma_store_4d(&map_x, xb, col0, ph2, row0 + dq, b);
+              if (p.has_a) tma_store_4d(&map_ahi, ab_hi, col0, ph2, row0 + dq, b);
+              tma_store_commit();
+            }
+          } else {
+            const long long orow = static_cast<long long>(row0 + lane) * p.out_rstride + t;  // this lane's output row
+            const long long off = static_cast<long long>(b) * p.epi.out_batch_stride + orow * p.out_cmod + col0;
+            if (orow >= 0 && (orow + 1) * p.out_cmod <= p.epi.out_extent) {
+              if (p.has_x) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  *reinterpret_cast<float4*>(p.epi.out_x + off + 4 * q) = *reinterpret_cast<const float4*>(xb + lane * 16 + ((q ^ swz64) << 2));
+              }
+              if (p.has_a) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+                  *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.epi.out_a0) + off + 8 * q) =
+                      *reinterpret_cast<const uint4*>(ab_hi + lane * 32 + ((q ^ swz32) << 4));
+              }
+            }
+            __syncwarp();  // the tiles are free again once every lane has read its row
+          }
+        } else if (lane == 0) {
+          if (p.has_x) tma_store_3d(&map_x, xb, nblk * N_T + c0, row0, b);
+          if (p.has_a) tma_store_3d(&map_ahi, ab_hi, nblk * N_T + c0, row0, b);
           tma_store_commit();
         }
       }

@@ -126,6 +126,7 @@ struct HgPlan {
   bool epi_tma = true;     // HG_EPI_TMA=0: always use the generic (LSU) epilogue in conv_tc
   bool epi_tma_convt = true;  // HG_EPI_TMA_CONVT=0: the polyphase upsamplers keep the generic epilogue
   int tc2_in_bufs = 2;     // HG_TC2_INBUFS=1: one residual tile in flight per epilogue warp of the CTA-pair kernel (round 1)
+  bool tc2_convt = true;   // HG_TC2_CONVT=0: upsamplers with several N blocks stay on the single-CTA kernel
   bool use_tc2 = true;     // HG_TC2=0: never use the CTA-pair (cta_group::2) kernel for the 256/128-channel convs
   bool force_ffma = false;  // HG_FORCE_FFMA=1: route every layer to the CUDA-core kernel
   // hg_stack_create: a plain chain of same-length Conv1d layers (no generator schedule); act/slope[i] is
