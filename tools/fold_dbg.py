@@ -3,7 +3,8 @@
 with parts of their work switched off through HG_FOLD_DBG (conv_pair_fold.cu, TcFoldParams::dbg):
 
     1 no MMAs   2 no global stores   4 no residual TMA   8 no slab TMA   16 no staging read-modify-write   32 no xt stores
-    64 no weight streaming (ring kernels)
+    64 no weight streaming (ring kernels)   256 no weight waits / producer   512 no weight-stage releases
+    1024 epilogue bodies off (hand-shakes only)
 
 The switches are compiled in only with -DHG_FOLD_DBG:
 

@@ -64,7 +64,8 @@ namespace hg {
 
 // Timing experiments (tools/fold_dbg.py; build with HG_NVCC_EXTRA=-DHG_FOLD_DBG): TcFoldParams::dbg bits drop parts
 // of the kernel's work — 1 MMAs, 2 global stores, 4 residual TMA, 8 slab TMA, 16 staging read-modify-write, 32 xt
-// stores, 64 weight streaming.  Results are wrong by construction; the shipped build compiles none of it.
+// stores, 64 weight streaming (the producer only signals), 256 weight waits and producer, 512 weight-stage releases,
+// 1024 epilogue bodies (hand-shakes only).  Results are wrong by construction; the shipped build compiles none of it.
 #ifdef HG_FOLD_DBG
 #define FOLD_DBG(bit) ((p.dbg & (bit)) != 0)
 #else
@@ -233,7 +234,7 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
 
   if (warp == 0) {
     // ------------------------------------------------ weight producer: blocks in the order the MMA issuer needs them
-    if (lane == 0 && n_my > 0 && !(RING && FOLD_DBG(1))) {
+    if (lane == 0 && n_my > 0 && !(RING && (FOLD_DBG(1) || FOLD_DBG(256)))) {
       if (!RING) {
         for (int cv = 0; cv < 2; ++cv) {
           const uint8_t* w = cv ? p.w2 : p.w1;
@@ -337,7 +338,7 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
         tc_fence_after();
         if (!FOLD_DBG(1))
           fold_issue_conv<C, K, S>(tmem_base + buf * ACC_COLS, slab_lo + buf * slab_buf16, slab_phase16, a1_row0_16, a1_shift16,
-                                   wst_lo, zero_lo, w_full, w_empty, cpar, !w_seen1);
+                                   wst_lo, zero_lo, w_full, w_empty, cpar, !w_seen1, (FOLD_DBG(256) ? 1 : 0) | (FOLD_DBG(512) ? 2 : 0));
         cpar ^= 1;
         umma_commit(&slab_empty[buf]);
         umma_commit(&d1_full[buf]);
@@ -354,7 +355,7 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
         if (!FOLD_DBG(1))
           fold_issue_conv<C, K, S>(tmem_base + (2 + buf) * ACC_COLS, t_lo + tbi * t_buf16, xt_phase16, a2_row0_16, a2_shift16,
                                    RING ? wst_lo : wst_lo + K * (WBLK >> 4), zero_lo, RING ? w_full : w_full + K,
-                                   RING ? w_empty : w_empty + K, cpar, !w_seen2);
+                                   RING ? w_empty : w_empty + K, cpar, !w_seen2, (FOLD_DBG(256) ? 1 : 0) | (FOLD_DBG(512) ? 2 : 0));
         cpar ^= 1;
         umma_commit(&t_empty[tbi]);
         umma_commit(&d2_full[buf]);
@@ -414,6 +415,12 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
       tc_fence_after();
       const uint32_t tbs = tb_s + tbi * t_bytes;
       const uint32_t tmem_acc = tmem_base + buf * ACC_COLS + lane_base;
+      if (FOLD_DBG(1024)) {  // hand-shakes only
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&d1_empty[buf]); mbar_arrive(&t_full[tbi]); }
+        return;
+      }
 #pragma unroll 1
       for (int j = sub; j < 8; j += 4) {
         uint32_t r[16];
@@ -484,6 +491,14 @@ conv_pair_fold_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_c
                             (static_cast<long long>(at.q0 + quarter * 32 + rsub) << 7) + n2;
       mbar_wait(&d2_full[buf], (i >> 1) & 1);
       tc_fence_after();
+      if (FOLD_DBG(1024)) {  // hand-shakes only
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&d2_empty[buf]);
+        mbar_wait(&res_bar[e], i & 1);
+        if (lane == 0 && next) prefetch_res(*next);
+        return;
+      }
       {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (2 + buf) * ACC_COLS + lane_base + c02, r);
