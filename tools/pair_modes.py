@@ -38,7 +38,7 @@ def main():
     for name, env in VARIANTS:
         old = {k: os.environ.get(k) for k in env}
         os.environ.update(env)
-        m = make_generator(fx.V1, precision="bf16").cuda()
+        m = make_generator(fx.V1, precision=os.environ.get("PRECISION", "bf16")).cuda()
         with torch.no_grad():
             y = m(mel)  # the plan (and its HG_* switches) is created here
         torch.cuda.synchronize()
